@@ -1,0 +1,280 @@
+/* streamsim_b200.h -- C ABI of libstreamsim_b200.so
+ *
+ * B200 (sm_100a) implementation of the per-star generate-and-observe path of
+ * LSSTDESC/stream_sim.  The reference has no FFI layer: its boundary is the
+ * Python API itself.  These entry points are what the
+ * bodies of the following reference methods bind to (see INTEGRATION.md for the
+ * ctypes stubs a maintainer would add):
+ *
+ *   ss_generate          <- StreamModel.sample            stream_sim/model.py:106-157
+ *   ss_rotate            <- StreamInjector.phi_to_radec   stream_sim/observed.py:478-575
+ *   ss_observe           <- StreamInjector.inject (body)  stream_sim/observed.py:146-291
+ *   ss_generate_observe  <- the three above fused, one pass, nothing materialised
+ *   ss_frame_fraction    <- StreamInjector._find_gc_frame trial body
+ *                           stream_sim/observed.py:661-668,700-718
+ *   ss_photo_error       <- Survey.get_photo_error        stream_sim/surveys.py:234-292
+ *   ss_efficiency        <- Survey.get_efficiency         stream_sim/surveys.py:399-493
+ *   ss_eval_function     <- BoundedFunction.__call__      stream_sim/functions.py:64-76
+ *
+ * Conventions
+ *   - plain C, POD structs, plain pointers and sizes; no torch types.
+ *   - every array pointer is a DEVICE pointer unless the name ends in _host.
+ *   - calls are stream-ordered on `stream` (a cudaStream_t passed as void*),
+ *     never allocate, never synchronise (the *_host variants are the exception:
+ *     they own the copies and return when the host buffers are complete).
+ *   - return 0 on success, a negative SS_E* code otherwise; ss_last_error()
+ *     gives a thread-local message.
+ *   - a NULL output column is simply not written; a NULL draw array means
+ *     "derive that draw from Philox4x32-10" (counter-based, see SS_DRAW_BLOCK_*).
+ */
+#ifndef STREAMSIM_B200_H
+#define STREAMSIM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SS_ABI_VERSION 3
+
+/* error codes */
+#define SS_OK 0
+#define SS_EINVAL (-1)   /* bad argument (message says which) */
+#define SS_ECUDA (-2)    /* CUDA runtime error (message carries cudaGetErrorString) */
+#define SS_ENODEV (-3)   /* no sm_100 device */
+
+/* pipeline stages (bit mask) */
+#define SS_STAGE_GENERATE 1u /* phi1, phi2, dist, mag_g, mag_r        (model.py:106-157) */
+#define SS_STAGE_ROTATE 2u   /* (phi1,phi2) -> (ra,dec)                (observed.py:573)  */
+#define SS_STAGE_OBSERVE 4u  /* pix, extinction, errors, noise, flags  (observed.py:146-291) */
+
+/* function kinds  (stream_sim/functions.py) */
+#define SS_FN_NONE 0
+#define SS_FN_CONSTANT 1 /* p[0]=value                                  :99-102  */
+#define SS_FN_LINE 2     /* p[0]=slope p[1]=intercept                   :130-133 */
+#define SS_FN_SINUSOID 3 /* p[0]=amplitude p[1]=period p[2]=phase p[3]=offset :164-169 */
+#define SS_FN_LINEAR 4   /* interp1d linear table: x[n], y[n], slope[n] :193-199 */
+#define SS_FN_SPLINE 5   /* natural cubic PPoly: x[n], c[4*(n-1)]       :255-274 */
+#define SS_FN_SPLINE_PRODUCT 6 /* sqrt(2pi)*I(x)*S(x): two SS_FN_SPLINE blocks :356-359 */
+
+/* samplers  (stream_sim/model.py:513-527) */
+#define SS_SAMPLER_GAUSSIAN 0
+#define SS_SAMPLER_UNIFORM 1
+
+/* density kinds (stream_sim/samplers.py) */
+#define SS_DENSITY_UNIFORM 0  /* :105-120 */
+#define SS_DENSITY_INVCDF 1   /* :55-76,158-161 */
+#define SS_DENSITY_GAUSSIAN 2 /* :123-138 */
+#define SS_DENSITY_NONE 3     /* phi1 always comes from SSCatalog.phi1 */
+
+/* band indices used in every [2] array below */
+#define SS_BAND_G 0
+#define SS_BAND_R 1
+
+/* output element type of the floating-point columns */
+#define SS_DTYPE_F64 0
+#define SS_DTYPE_F32 1
+
+/* Philox4x32-10 draw blocks: counter = (star_lo, star_hi, block, 0),
+ * key = (seed_lo, seed_hi).  Each block yields two 53-bit uniforms (U0,U1):
+ *   block 0: U0 = u_phi1, U1 = u_mass
+ *   block 1: Gaussian samplers use Box-Muller(U0,U1) -> (z_phi2, z_dist);
+ *            Uniform samplers use U0 for phi2 and U1 for dist
+ *   block 2: Box-Muller(U0,U1) -> (z_r, z_g)   flux noise, r then g
+ *   block 3: U0 = u_det (completeness), U1 = u_det2 (detection-only)
+ *   block 4: Box-Muller(U0,U1).first -> z_phi1 (Gaussian density only)
+ * A star's draws depend only on (seed, global star index): any sharding of the
+ * index range over launches or GPUs gives identical per-star results. */
+#define SS_DRAW_BLOCK_POS 0
+#define SS_DRAW_BLOCK_TRACK 1
+#define SS_DRAW_BLOCK_FLUX 2
+#define SS_DRAW_BLOCK_DETECT 3
+#define SS_DRAW_BLOCK_DENSITY_Z 4
+
+/* counters written (atomically accumulated) into SSOut.counters */
+#define SS_CNT_TOTAL 0
+#define SS_CNT_OBSERVED 1     /* flag_observed                                  */
+#define SS_CNT_PERFECT 2      /* flag_perfect_galstarsep                        */
+#define SS_CNT_BADMAG_G 3     /* flux_obs <= 0 or NaN in g ("BAD_MAG")          */
+#define SS_CNT_BADMAG_R 4
+#define SS_CNT_UNSEEN 5       /* maglim NaN in the completeness band            */
+#define SS_CNT_DOMAIN 6       /* !(scale >= 0) in a sampler -> scipy ValueError */
+#define SS_CNT_BADCOORD 7     /* ra/dec NaN or |dec| > 90 -> healpy ValueError  */
+#define SS_CNT_INSIDE 8       /* ss_frame_fraction: stars inside the mask       */
+#define SS_N_COUNTERS 16
+#define SS_HIST_BINS 256
+#define SS_N_HIST 5           /* phi1, phi2, dist, mag_g, g-r                   */
+/* SSOut.counters layout: [SS_N_COUNTERS] then SS_N_HIST x [SS_HIST_BINS], uint64 */
+#define SS_COUNTERS_LEN (SS_N_COUNTERS + SS_N_HIST * SS_HIST_BINS)
+
+typedef struct SSFunc {
+  int32_t kind;
+  int32_t n;      /* knots */
+  int32_t x_off;  /* offsets into SSTables.blob, in doubles */
+  int32_t c_off;  /* LINEAR: y[n] then slope[n]; SPLINE: c[4*(n-1)], highest power first */
+  double xmin, xmax; /* result is NaN outside [xmin,xmax] */
+  double p[4];
+  int32_t n2, x2_off, c2_off, pad_; /* second spline of SS_FN_SPLINE_PRODUCT */
+} SSFunc;
+
+typedef struct SSParams {
+  /* ---- generate: density (samplers.py) */
+  int32_t density_kind;
+  int32_t cdf_n;        /* grid points (reference: 100000)                       */
+  int32_t cdf_guide_n;  /* power of two; guide has cdf_guide_n+1 int32 entries   */
+  int32_t cdf_identity; /* 1: interp1d's mergesort permutation is the identity   */
+  double density_lo, density_hi; /* uniform: xmin,xmax; invcdf: grid start,stop; gaussian: mu,sigma */
+  double grid_step;     /* np.linspace step                                      */
+  double cdf_first, cdf_last; /* sorted cdf[0], cdf[n-1]; outside -> index 0     */
+  /* ---- generate: track and distance modulus (model.py:500-544) */
+  SSFunc track_center, track_spread, dist_center, dist_spread;
+  int32_t track_sampler, dist_sampler;
+  int32_t has_dist, has_iso;
+  /* ---- generate: isochrone (model.py:575-604; ugali imf.sample + interp1d) */
+  int32_t iso_n;        /* rows of (mass_init, mag_1, mag_2), sorted by mass      */
+  int32_t iso_mass_off, iso_mag_off[2], iso_slope_off[2]; /* blob offsets, doubles */
+  int32_t imf_n;        /* IMF CDF steps (ugali: 10000)                           */
+  int32_t imf_cdf_off;  /* blob offset of cdf[imf_n]                              */
+  int32_t imf_guide_n;  /* power of two                                           */
+  int32_t imf_guide_off;/* blob offset IN INT32 UNITS of guide[imf_guide_n+1]     */
+  int32_t cdf_guide_off;/* blob offset IN INT32 UNITS of guide[cdf_guide_n+1]     */
+  int32_t pad0_;
+  double imf_mass_lo, imf_mass_hi, imf_mass_step; /* np.linspace(lo,hi,imf_n)     */
+  /* ---- rotate: R rows = (origin, pole x origin, pole), ICRS -> stream frame */
+  double R[9];
+  /* ---- observe */
+  int32_t nside_pix;        /* inject(nside=...) ; only used for SSOut.pix        */
+  int32_t nside_ebv;
+  int32_t nside_maglim[2];
+  int32_t band_present[2];  /* band listed in inject(bands=...); 'r' is mandatory  */
+  int32_t completeness_band;
+  int32_t dust_correction, perfect_galstarsep;
+  int32_t snr_cut[2];       /* band in detection_mag_cut (and in bands)           */
+  int32_t nest;             /* 0 RING (the reference), 1 NESTED maps              */
+  double coeff_extinc[2], saturation[2], sys_error[2];
+  double delta_saturation;
+  double snr_err_max;       /* largest e with fl(1/e) >= SNR_min (observed.py:267-279) */
+  double log_err_at_dsat;   /* f(dsat)          surveys.py:278                    */
+  double err_bright;        /* 10**f(dsat-1)    surveys.py:284                    */
+  SSFunc photo_error;       /* SS_FN_LINEAR, fill 1.0 both sides (surveys.py:1412-1417) */
+  SSFunc completeness;      /* SS_FN_LINEAR, fill 0.0           (surveys.py:1361-1366) */
+  SSFunc detection;         /* detection-only table, used when perfect_galstarsep */
+  /* ---- histograms: bin = floor((v - lo) * inv_width), dropped if outside */
+  int32_t hist_enable, pad1_;
+  double hist_lo[SS_N_HIST], hist_inv_width[SS_N_HIST];
+} SSParams;
+
+typedef struct SSTables {
+  const void* blob;          /* packed small tables (doubles first, int32 guides after) */
+  int64_t blob_bytes;        /* multiple of 16                                    */
+  const double* cdf_pairs;   /* [cdf_n][2] = (sorted cdf_j, slope_j)              */
+  const int32_t* cdf_perm;   /* [cdf_n] original index of sorted entry j; NULL if identity */
+  const double* grid;        /* [cdf_n] explicit phi1 grid, or NULL = start + j*step */
+} SSTables;
+
+typedef struct SSMaps {
+  const double* ebv;         /* [12*nside_ebv^2]                                  */
+  const double* maglim[2];   /* [12*nside_maglim[b]^2], NaN = unseen              */
+  const uint8_t* mask;       /* ss_frame_fraction only: [12*nside_mask^2]         */
+  int32_t nside_mask, pad_;
+} SSMaps;
+
+typedef struct SSCatalog {   /* per-star inputs of the stages that are not run */
+  /* ROTATE without GENERATE reads phi1/phi2.  GENERATE treats non-NULL phi1 / phi2 /
+   * dist as a partially filled catalog: finite entries are kept, NaN entries are
+   * sampled (StreamModel.complete_catalog, reference model.py:261-298). */
+  const double* phi1;
+  const double* phi2;
+  const double* dist;
+  const double* ra;          /* OBSERVE without ROTATE                           */
+  const double* dec;
+  const double* mag[2];      /* OBSERVE without GENERATE (true apparent mags)    */
+} SSCatalog;
+
+typedef struct SSDraws {     /* injected draws; NULL -> Philox */
+  const double* u_phi1;      /* z for SS_DENSITY_GAUSSIAN                        */
+  const double* n_phi2;      /* z (Gaussian sampler) or u (Uniform sampler)      */
+  const double* n_dist;
+  const double* u_mass;
+  const double* z_flux[2];   /* per band                                         */
+  const double* u_det;
+  const double* u_det2;
+} SSDraws;
+
+typedef struct SSOut {
+  int32_t dtype, pad_;       /* SS_DTYPE_*: element type of the columns below    */
+  void* phi1;  void* phi2;  void* dist;
+  void* mag[2];              /* true apparent magnitudes (no extinction)         */
+  void* ra;  void* dec;
+  void* mag_obs[2];          /* NaN where the reference writes "BAD_MAG"         */
+  void* magerr[2];
+  uint8_t* flag_observed;
+  uint8_t* flag_perfect;
+  int64_t* pix;              /* ang2pix at nside_pix                             */
+  unsigned long long* counters; /* [SS_COUNTERS_LEN], accumulated, or NULL       */
+} SSOut;
+
+int ss_abi_version(void);
+const char* ss_last_error(void);
+/* sizeof() of SSFunc, SSParams, SSTables, SSMaps, SSCatalog, SSDraws, SSOut, in that
+ * order: lets a binding verify its struct mirrors. */
+int ss_struct_sizes(int32_t* sizes7);
+/* dynamic shared memory the star kernel will request for this blob (0 = blob
+ * stays in global memory) and the grid it will launch for n stars. */
+int ss_launch_info(int64_t blob_bytes, uint64_t n, int32_t* smem_bytes, int32_t* grid, int32_t* block);
+
+/* Generic launcher: run `stages` for stars [star_offset, star_offset+n). */
+int ss_run(uint32_t stages, const SSParams* p, const SSTables* t, const SSMaps* m,
+           const SSCatalog* in, const SSDraws* d, const SSOut* out,
+           uint64_t n, uint64_t star_offset, uint64_t seed, void* stream);
+
+/* Named entry points = ss_run with a fixed stage mask. */
+int ss_generate(const SSParams* p, const SSTables* t, const SSDraws* d, const SSOut* out,
+                uint64_t n, uint64_t star_offset, uint64_t seed, void* stream);
+int ss_rotate(const SSParams* p, const SSCatalog* in, const SSOut* out, uint64_t n, void* stream);
+int ss_observe(const SSParams* p, const SSTables* t, const SSMaps* m, const SSCatalog* in,
+               const SSDraws* d, const SSOut* out,
+               uint64_t n, uint64_t star_offset, uint64_t seed, void* stream);
+int ss_generate_observe(const SSParams* p, const SSTables* t, const SSMaps* m,
+                        const SSDraws* d, const SSOut* out,
+                        uint64_t n, uint64_t star_offset, uint64_t seed, void* stream);
+
+/* One trial of the great-circle frame search: rotate (phi1,phi2) with p->R,
+ * ang2pix at m->nside_mask, count stars whose mask byte is non-zero into
+ * counters[SS_CNT_INSIDE] (and n into counters[SS_CNT_TOTAL]). */
+int ss_frame_fraction(const SSParams* p, const SSMaps* m, const SSCatalog* in,
+                      unsigned long long* counters, uint64_t n, void* stream);
+
+/* Element-wise survey getters on device arrays (fp64 in, fp64 out). */
+int ss_photo_error(const SSParams* p, const SSTables* t, int32_t band,
+                   const double* mag, const double* maglim, double* out, uint64_t n, void* stream);
+int ss_efficiency(const SSParams* p, const SSTables* t, int32_t band, int32_t detection_only,
+                  const double* mag, const double* maglim, double* out, uint64_t n, void* stream);
+int ss_eval_function(const SSFunc* f, const SSTables* t, const double* x, double* out,
+                     uint64_t n, void* stream);
+int ss_ang2pix(int32_t nside, int32_t nest, const double* lon_deg, const double* lat_deg,
+               int64_t* pix, uint64_t n, void* stream);
+
+/* Host-buffer variant of ss_generate_observe: every SSOut column pointer (and
+ * counters) is a HOST pointer (pinned for full speed).  Stars are produced in
+ * chunks into the caller-provided device workspace and copied back on a second
+ * stream while the next chunk computes.  Returns when `out` is complete.
+ *   workspace: device buffer of workspace_bytes >= ss_host_workspace_bytes(chunk, dtype)
+ */
+int64_t ss_host_workspace_bytes(uint64_t chunk, int32_t dtype);
+int ss_generate_observe_host(const SSParams* p, const SSTables* t, const SSMaps* m,
+                             const SSOut* out_host, uint64_t n, uint64_t star_offset,
+                             uint64_t seed, void* workspace, int64_t workspace_bytes,
+                             uint64_t chunk);
+/* Host-buffer variant of ss_observe: catalog columns (ra, dec, mag[2]) and all
+ * outputs are HOST pointers; same chunked two-stream pipeline. */
+int ss_observe_host(const SSParams* p, const SSTables* t, const SSMaps* m,
+                    const SSCatalog* in_host, const SSOut* out_host, uint64_t n,
+                    uint64_t star_offset, uint64_t seed, void* workspace,
+                    int64_t workspace_bytes, uint64_t chunk);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STREAMSIM_B200_H */

@@ -1,0 +1,259 @@
+// Device building blocks of the per-star path: Philox4x32-10, table search and
+// interpolation with NumPy/SciPy semantics, HEALPix ang2pix.  sm_100a only.
+//
+// Arithmetic that feeds an integer index or a comparison (pixel numbers, CDF
+// index, efficiency compare) is written with explicit round-to-nearest
+// intrinsics so nvcc cannot contract a*b+c into an FMA: the reference runs
+// un-fused IEEE double arithmetic (NumPy / healpix_cxx on x86-64).
+#pragma once
+#include <stdint.h>
+#include "../../include/streamsim_b200.h"
+
+namespace ss {
+
+__device__ __forceinline__ double nan_d() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+// ---------------------------------------------------------------- Philox4x32-10
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+// two 32-bit words -> double in [0,1) carrying 53 random bits (exact in fp64)
+__device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
+  return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+__device__ __forceinline__ void philox_pair(unsigned long long star, uint32_t block,
+                                            unsigned long long seed, double& u0, double& u1) {
+  uint4 c = make_uint4((uint32_t)star, (uint32_t)(star >> 32), block, 0u);
+  c = philox4x32_10(c, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  u0 = u53(c.x, c.y);
+  u1 = u53(c.z, c.w);
+}
+
+__device__ __forceinline__ void box_muller(double ua, double ub, double& z0, double& z1) {
+  const double r = sqrt(-2.0 * log(1.0 - ua));
+  double s, c;
+  sincospi(2.0 * ub, &s, &c);
+  z0 = r * c;
+  z1 = r * s;
+}
+
+// ---------------------------------------------------------------- table search
+// last j in [lo, hi) with xp[j] <= x.  Requires xp[lo] <= x and (hi == n or xp[hi] > x).
+__device__ __forceinline__ int search_le(const double* __restrict__ xp, int lo, int hi, double x) {
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (xp[mid] <= x) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// np.interp(x, xp, fp, left=fill_lo, right=fill_hi) with host-precomputed slopes
+// (numpy/_core/src/multiarray/compiled_base.c arr_interp): NaN x -> NaN, exact knot
+// hit -> fp[j], otherwise slope*(x - xp[j]) + fp[j] in un-fused double arithmetic.
+__device__ __forceinline__ double lin_eval(const double* __restrict__ xp,
+                                           const double* __restrict__ fp,
+                                           const double* __restrict__ sl, int n, double x,
+                                           double fill_lo, double fill_hi) {
+  if (x != x) return x;
+  if (x < xp[0]) return fill_lo;
+  if (x > xp[n - 1]) return fill_hi;
+  const int j = search_le(xp, 0, n, x);
+  const double xj = xp[j], fj = fp[j];
+  if (j == n - 1 || xj == x) return fj;
+  return __dadd_rn(__dmul_rn(sl[j], __dsub_rn(x, xj)), fj);
+}
+
+// scipy CubicSpline(bc_type='natural', extrapolate=False)(x): PPoly in powers of
+// (x - x_j), coefficients highest power first, NaN outside [x_0, x_{n-1}].
+__device__ __forceinline__ double spline_eval(const double* __restrict__ xk,
+                                              const double* __restrict__ c, int n, double x) {
+  if (!(x >= xk[0] && x <= xk[n - 1])) return nan_d();
+  int j = search_le(xk, 0, n, x);
+  if (j > n - 2) j = n - 2;
+  const double s = x - xk[j];
+  const double* cj = c + 4 * j;
+  return ((cj[0] * s + cj[1]) * s + cj[2]) * s + cj[3];
+}
+
+// BoundedFunction.__call__ (reference functions.py:64-76)
+__device__ __forceinline__ double fn_eval(const SSFunc& f, const double* __restrict__ tab, double x) {
+  double y;
+  switch (f.kind) {
+    case SS_FN_CONSTANT:
+      y = f.p[0];
+      break;
+    case SS_FN_LINE:
+      y = __dadd_rn(__dmul_rn(f.p[0], x), f.p[1]);
+      break;
+    case SS_FN_SINUSOID: {
+      const double norm = f.p[0] / 2.0;
+      const double arg = __ddiv_rn(__dmul_rn(6.283185307179586, __dsub_rn(x, f.p[2])), f.p[1]);
+      y = __dadd_rn(__dadd_rn(__dmul_rn(norm, cos(arg)), norm), f.p[3]);
+      break;
+    }
+    case SS_FN_LINEAR:
+      y = lin_eval(tab + f.x_off, tab + f.c_off, tab + f.c_off + f.n, f.n, x, nan_d(), nan_d());
+      break;
+    case SS_FN_SPLINE:
+      y = spline_eval(tab + f.x_off, tab + f.c_off, f.n, x);
+      break;
+    case SS_FN_SPLINE_PRODUCT:
+      // LinearDensityCubicSplineInterpolation has no bounds mask of its own (functions.py:349-359)
+      return 2.5066282746310002 * spline_eval(tab + f.x_off, tab + f.c_off, f.n, x) *
+             spline_eval(tab + f.x2_off, tab + f.c2_off, f.n2, x);
+    default:
+      y = nan_d();
+  }
+  return (x >= f.xmin && x <= f.xmax) ? y : nan_d();
+}
+
+// ---------------------------------------------------------------- HEALPix
+// healpy.ang2pix(nside, lon, lat, lonlat=True) = healpix_cxx T_Healpix_Base<int64>::
+// ang2pix -> loc2pix.  The angle preparation is shared by every nside.
+struct HpLoc {
+  double z, tt, sth;
+  bool have_sth, valid;
+};
+
+__device__ __forceinline__ HpLoc hp_locate(double lon_deg, double lat_deg) {
+  const double D2R = 0.017453292519943295;      // NPY_PI/180 (np.radians)
+  const double HALFPI = 1.5707963267948966;     // np.pi/2
+  const double INV_HALFPI = 0.6366197723675813430755350534900574;
+  HpLoc L;
+  const double theta = __dsub_rn(HALFPI, __dmul_rn(lat_deg, D2R));
+  const double phi = __dmul_rn(lon_deg, D2R);
+  // healpy check_theta_valid: 0 <= theta <= pi + 1e-5; NaN fails both
+  L.valid = (theta >= 0.0) && (theta <= 3.141592653589793 + 1e-5) && (phi == phi) &&
+            (fabs(phi) < 1e300);
+  L.have_sth = (theta < 0.01) || (theta > 3.14159 - 0.01);
+  L.z = cos(theta);
+  L.sth = L.have_sth ? sin(theta) : 0.0;
+  const double v = __dmul_rn(phi, INV_HALFPI);
+  double tt;
+  if (v >= 0.0) {
+    tt = (v < 4.0) ? v : fmod(v, 4.0);
+  } else {
+    tt = fmod(v, 4.0) + 4.0;
+    if (tt == 4.0) tt = 0.0;
+  }
+  L.tt = tt;
+  return L;
+}
+
+__device__ __forceinline__ double hp_polar_tmp(const HpLoc& L, double za, double ns) {
+  return (za < 0.99 || !L.have_sth) ? __dmul_rn(ns, sqrt(__dmul_rn(3.0, __dsub_rn(1.0, za))))
+                                    : __ddiv_rn(__dmul_rn(ns, L.sth), sqrt(__ddiv_rn(__dadd_rn(1.0, za), 3.0)));
+}
+
+__device__ __forceinline__ long long hp_ring(const HpLoc& L, long long nside) {
+  const double ns = (double)nside;
+  const double za = fabs(L.z);
+  if (za <= 2.0 / 3.0) {
+    const long long nl4 = 4 * nside;
+    const double t1 = __dmul_rn(ns, __dadd_rn(0.5, L.tt));
+    const double t2 = __dmul_rn(__dmul_rn(ns, L.z), 0.75);
+    const long long jp = (long long)__dsub_rn(t1, t2);
+    const long long jm = (long long)__dadd_rn(t1, t2);
+    const long long ir = nside + 1 + jp - jm;
+    const long long kshift = 1 - (ir & 1);
+    const long long t = jp + jm - nside + kshift + 1 + nl4 + nl4;
+    const long long ip = ((nside & (nside - 1)) == 0 && nside > 1) ? ((t >> 1) & (nl4 - 1))
+                                                                   : ((t >> 1) % nl4);
+    return 2 * nside * (nside - 1) + (ir - 1) * nl4 + ip;
+  }
+  const double tp = __dsub_rn(L.tt, (double)(long long)L.tt);
+  const double tmp = hp_polar_tmp(L, za, ns);
+  const long long jp = (long long)__dmul_rn(tp, tmp);
+  const long long jm = (long long)__dmul_rn(__dsub_rn(1.0, tp), tmp);
+  const long long ir = jp + jm + 1;
+  const long long ip = (long long)__dmul_rn(L.tt, (double)ir);
+  return (L.z > 0) ? 2 * ir * (ir - 1) + ip : 12 * nside * nside - 2 * ir * (ir + 1) + ip;
+}
+
+__device__ __forceinline__ unsigned long long hp_spread_bits(unsigned long long v) {
+  v = (v | (v << 16)) & 0x0000FFFF0000FFFFULL;
+  v = (v | (v << 8)) & 0x00FF00FF00FF00FFULL;
+  v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0FULL;
+  v = (v | (v << 2)) & 0x3333333333333333ULL;
+  v = (v | (v << 1)) & 0x5555555555555555ULL;
+  return v;
+}
+
+__device__ __forceinline__ long long hp_nest(const HpLoc& L, long long nside) {
+  const double ns = (double)nside;
+  const double za = fabs(L.z);
+  const int order = 63 - __clzll(nside);
+  long long ix, iy, face;
+  if (za <= 2.0 / 3.0) {
+    const double t1 = __dmul_rn(ns, __dadd_rn(0.5, L.tt));
+    const double t2 = __dmul_rn(__dmul_rn(ns, L.z), 0.75);
+    const long long jp = (long long)__dsub_rn(t1, t2);
+    const long long jm = (long long)__dadd_rn(t1, t2);
+    const long long ifp = jp >> order, ifm = jm >> order;
+    face = (ifp == ifm) ? (ifp | 4) : ((ifp < ifm) ? ifp : (ifm + 8));
+    ix = jm & (nside - 1);
+    iy = nside - (jp & (nside - 1)) - 1;
+  } else {
+    long long ntt = (long long)L.tt;
+    if (ntt > 3) ntt = 3;
+    const double tp = __dsub_rn(L.tt, (double)ntt);
+    const double tmp = hp_polar_tmp(L, za, ns);
+    long long jp = (long long)__dmul_rn(tp, tmp);
+    long long jm = (long long)__dmul_rn(__dsub_rn(1.0, tp), tmp);
+    if (jp > nside - 1) jp = nside - 1;
+    if (jm > nside - 1) jm = nside - 1;
+    if (L.z >= 0) { ix = nside - jm - 1; iy = nside - jp - 1; face = ntt; }
+    else { ix = jp; iy = jm; face = ntt + 8; }
+  }
+  return (face << (2 * order)) + (long long)(hp_spread_bits((unsigned long long)ix) |
+                                             (hp_spread_bits((unsigned long long)iy) << 1));
+}
+
+__device__ __forceinline__ long long hp_pix(const HpLoc& L, long long nside, int nest) {
+  return nest ? hp_nest(L, nside) : hp_ring(L, nside);
+}
+
+// ---------------------------------------------------------------- survey getters
+// Survey.get_photo_error (reference surveys.py:270-290)
+__device__ __forceinline__ double photo_error(const SSParams& p, const double* __restrict__ tab,
+                                              int band, double mag, double maglim) {
+  const double delta = __dsub_rn(mag, maglim);
+  const double sat = p.saturation[band];
+  double stat;
+  if (mag < sat) {
+    stat = p.err_bright;
+  } else {
+    const SSFunc& f = p.photo_error;
+    const double loge = (delta <= p.delta_saturation && mag >= sat)
+                            ? p.log_err_at_dsat
+                            : lin_eval(tab + f.x_off, tab + f.c_off, tab + f.c_off + f.n, f.n,
+                                       delta, 1.0, 1.0);
+    stat = exp10(loge);
+  }
+  const double sys = p.sys_error[band];
+  return sqrt(__dadd_rn(__dmul_rn(stat, stat), __dmul_rn(sys, sys)));
+}
+
+// Survey.get_efficiency (reference surveys.py:473-493)
+__device__ __forceinline__ double efficiency(const SSParams& p, const SSFunc& f,
+                                             const double* __restrict__ tab, int band,
+                                             double mag, double maglim) {
+  const double sat = p.saturation[band];
+  if (maglim < sat || maglim != maglim) return 0.0;
+  if (mag < sat) return 0.0;
+  const double delta = __dsub_rn(mag, maglim);
+  if (mag > sat && delta <= p.delta_saturation) return 1.0;
+  return lin_eval(tab + f.x_off, tab + f.c_off, tab + f.c_off + f.n, f.n, delta, 0.0, 0.0);
+}
+
+}  // namespace ss

@@ -1,0 +1,970 @@
+// libstreamsim_b200.so -- fused per-star generate -> rotate -> observe kernel for
+// NVIDIA B200 (sm_100a) and its C ABI (include/streamsim_b200.h).
+//
+// One persistent CTA per SM.  The small lookup tables (track / distance-modulus
+// knots, isochrone, IMF CDF, efficiency and photo-error curves, search guides)
+// are packed by the host into one blob that each CTA pulls into shared memory
+// with a single TMA bulk copy (cp.async.bulk + mbarrier); the 100000-point
+// phi1 CDF and the HEALPix maps stay in HBM/L2 and are read through the
+// read-only path.  Every star is independent: thread t handles stars
+// t, t+T, t+2T, ... so that each output column is written as fully coalesced
+// 128-byte lines.  Randomness is counter-based (Philox4x32-10 keyed by the
+// global star index) so results do not depend on the launch geometry or on how
+// the index range is sharded across GPUs.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "device_math.cuh"
+
+#define SS_BLOCK 512
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, const char* detail = "") {
+  snprintf(g_err, sizeof(g_err), fmt, detail);
+  return code;
+}
+
+#define SS_CUDA(call)                                                        \
+  do {                                                                       \
+    cudaError_t e_ = (call);                                                 \
+    if (e_ != cudaSuccess) return fail(SS_ECUDA, #call ": %s", cudaGetErrorString(e_)); \
+  } while (0)
+
+struct KArgs {
+  SSParams p;
+  SSTables t;
+  SSMaps m;
+  SSCatalog in;
+  SSDraws d;
+  SSOut o;
+  unsigned long long n, offset, seed;
+  int blob_in_smem;
+  uint32_t blob_bytes;
+};
+
+// ---------------------------------------------------------------- smem staging
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// Pull `bytes` (multiple of 16) from global into shared memory with the TMA bulk
+// engine; every thread of the CTA returns once the bytes have landed.
+__device__ __forceinline__ void stage_blob(void* dst, const void* src, uint32_t bytes,
+                                           unsigned long long* bar) {
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+    // the bulk engine takes at most 2^20-1 bytes of tx count per barrier phase; the
+    // blob is < 227 KB.  Issue in <= 64 KB pieces.
+    uint32_t done = 0;
+    while (done < bytes) {
+      const uint32_t piece = min(bytes - done, 65536u);
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+          ::"r"(smem_u32((const char*)dst + done)), "l"((const char*)src + done), "r"(piece),
+          "r"(smem_u32(bar))
+          : "memory");
+      done += piece;
+    }
+  }
+  // bounded wait: a lost transaction traps instead of hanging the GPU
+  uint32_t ok = 0;
+  for (int spin = 0; spin < (1 << 22) && !ok; ++spin) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n"
+        " selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar))
+        : "memory");
+  }
+  if (!ok) __trap();
+}
+
+// ---------------------------------------------------------------- helpers
+template <typename T>
+__device__ __forceinline__ void put(void* col, unsigned long long i, double v) {
+  if (col) reinterpret_cast<T*>(col)[i] = (T)v;
+}
+
+// TrackModel.sample (reference model.py:513-544): value = draw*scale + loc
+__device__ __forceinline__ double track_sample(const SSFunc& fc, const SSFunc& fs, int sampler,
+                                               const double* tab, double x, double draw,
+                                               unsigned& domain_err) {
+  const double c = ss::fn_eval(fc, tab, x);
+  const double s = ss::fn_eval(fs, tab, x);
+  if (sampler == SS_SAMPLER_GAUSSIAN) {
+    if (!(s >= 0.0)) domain_err++;
+    return __dadd_rn(__dmul_rn(draw, s), c);
+  }
+  const double lo = __dsub_rn(c, s);
+  const double hi = __dadd_rn(lo, __dmul_rn(2.0, s));
+  const double scale = __dsub_rn(hi, lo);
+  if (!(scale >= 0.0)) domain_err++;
+  return __dadd_rn(__dmul_rn(draw, scale), lo);
+}
+
+// inverse_transform_sample (reference samplers.py:55-76) on the host-built tables
+__device__ __forceinline__ double invcdf_phi1(const KArgs& a, const int32_t* __restrict__ itab,
+                                              double u) {
+  const SSParams& p = a.p;
+  const int n = p.cdf_n;
+  double y;
+  if (!(u >= p.cdf_first && u <= p.cdf_last)) {
+    y = (u != u) ? u : 0.0;  // fill_value=0.0 outside; NaN stays NaN
+  } else {
+    const double2* __restrict__ cp = reinterpret_cast<const double2*>(a.t.cdf_pairs);
+    int lo = 0, hi = n;
+    if (p.cdf_guide_n > 0 && u >= 0.0 && u < 1.0) {
+      const int32_t* guide = itab + p.cdf_guide_off;
+      const int g = (int)(u * (double)p.cdf_guide_n);
+      lo = guide[g];
+      hi = guide[g + 1] + 1;
+      if (hi > n) hi = n;
+    }
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(&cp[mid].x) <= u) lo = mid; else hi = mid;
+    }
+    const double2 e = __ldg(&cp[lo]);
+    const double base = p.cdf_identity ? (double)lo : (double)__ldg(&a.t.cdf_perm[lo]);
+    y = (lo == n - 1 || e.x == u) ? base : __dadd_rn(__dmul_rn(e.y, __dsub_rn(u, e.x)), base);
+  }
+  if (y != y) return y;
+  const long long idx = __double2ll_rn(y);  // np.rint: half to even
+  if (a.t.grid) return __ldg(&a.t.grid[idx]);
+  return (idx == n - 1) ? p.density_hi
+                        : __dadd_rn(__dmul_rn((double)idx, p.grid_step), p.density_lo);
+}
+
+// ugali imf.sample + isochrone interp1d (reference model.py:590-602)
+__device__ __forceinline__ void iso_sample(const SSParams& p, const double* __restrict__ tab,
+                                           const int32_t* __restrict__ itab, double u,
+                                           double& m1, double& m2, unsigned& domain_err) {
+  const double* __restrict__ cdf = tab + p.imf_cdf_off;
+  const int n = p.imf_n;
+  if (!(u >= cdf[0] && u <= cdf[n - 1])) {  // interp1d(bounds_error=True) raises
+    domain_err++;
+    m1 = m2 = ss::nan_d();
+    return;
+  }
+  int lo = 0, hi = n;
+  if (p.imf_guide_n > 0 && u >= 0.0 && u < 1.0) {
+    const int32_t* guide = itab + p.imf_guide_off;
+    const int g = (int)(u * (double)p.imf_guide_n);
+    lo = guide[g];
+    hi = min(guide[g + 1] + 1, n);
+  }
+  const int j = ss::search_le(cdf, lo, hi, u);
+  const double mj = (j == n - 1) ? p.imf_mass_hi
+                                 : __dadd_rn(__dmul_rn((double)j, p.imf_mass_step), p.imf_mass_lo);
+  double mass;
+  const double cj = cdf[j];
+  if (j == n - 1 || cj == u) {
+    mass = mj;
+  } else {
+    const double mj1 = (j + 1 == n - 1)
+                           ? p.imf_mass_hi
+                           : __dadd_rn(__dmul_rn((double)(j + 1), p.imf_mass_step), p.imf_mass_lo);
+    const double slope = __ddiv_rn(__dsub_rn(mj1, mj), __dsub_rn(cdf[j + 1], cj));
+    mass = __dadd_rn(__dmul_rn(slope, __dsub_rn(u, cj)), mj);
+  }
+  const double* __restrict__ mi = tab + p.iso_mass_off;
+  const int ni = p.iso_n;
+  if (!(mass >= mi[0] && mass <= mi[ni - 1])) {
+    domain_err++;
+    m1 = m2 = ss::nan_d();
+    return;
+  }
+  const int k = ss::search_le(mi, 0, ni, mass);
+  const double xk = mi[k];
+  if (k == ni - 1 || xk == mass) {
+    m1 = tab[p.iso_mag_off[0] + k];
+    m2 = tab[p.iso_mag_off[1] + k];
+  } else {
+    const double dx = __dsub_rn(mass, xk);
+    m1 = __dadd_rn(__dmul_rn(tab[p.iso_slope_off[0] + k], dx), tab[p.iso_mag_off[0] + k]);
+    m2 = __dadd_rn(__dmul_rn(tab[p.iso_slope_off[1] + k], dx), tab[p.iso_mag_off[1] + k]);
+  }
+}
+
+// ---------------------------------------------------------------- the star kernel
+template <uint32_t ST, typename OutT>
+__global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ KArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_blob[];
+  __shared__ unsigned long long s_bar;
+  __shared__ unsigned int s_cnt[SS_N_COUNTERS];
+  __shared__ unsigned int s_hist[SS_N_HIST * SS_HIST_BINS];
+
+  const SSParams& p = a.p;
+  const bool want_cnt = a.o.counters != nullptr;
+  const bool want_hist = want_cnt && p.hist_enable;
+
+  for (int i = threadIdx.x; i < SS_N_COUNTERS; i += blockDim.x) s_cnt[i] = 0;
+  if (want_hist)
+    for (int i = threadIdx.x; i < SS_N_HIST * SS_HIST_BINS; i += blockDim.x) s_hist[i] = 0;
+
+  const double* tab;
+  if (a.blob_in_smem) {
+    stage_blob(smem_blob, a.t.blob, a.blob_bytes, &s_bar);
+    tab = reinterpret_cast<const double*>(smem_blob);
+  } else {
+    tab = reinterpret_cast<const double*>(a.t.blob);
+  }
+  const int32_t* itab = reinterpret_cast<const int32_t*>(tab);
+  __syncthreads();
+
+  unsigned c_obs = 0, c_perf = 0, c_bad_g = 0, c_bad_r = 0, c_unseen = 0, c_dom = 0, c_coord = 0,
+           c_tot = 0;
+
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n;
+       i += stride) {
+    const unsigned long long gi = a.offset + i;
+    c_tot++;
+    double phi1 = 0, phi2 = 0, dist = ss::nan_d(), mag_g = ss::nan_d(), mag_r = ss::nan_d();
+    double ra = 0, dec = 0;
+
+    // ------------------------------------------------ generate (model.py:106-157)
+    if (ST & SS_STAGE_GENERATE) {
+      double u_phi1, u_mass;
+      if (a.d.u_phi1 && (a.d.u_mass || !p.has_iso)) {
+        u_phi1 = a.d.u_phi1[i];
+        u_mass = p.has_iso ? a.d.u_mass[i] : 0.0;
+      } else {
+        ss::philox_pair(gi, SS_DRAW_BLOCK_POS, a.seed, u_phi1, u_mass);
+        if (a.d.u_phi1) u_phi1 = a.d.u_phi1[i];
+        if (a.d.u_mass) u_mass = a.d.u_mass[i];
+      }
+      const double phi1_given = a.in.phi1 ? a.in.phi1[i] : ss::nan_d();
+      if (phi1_given == phi1_given) {
+        phi1 = phi1_given;
+      } else if (p.density_kind == SS_DENSITY_UNIFORM) {
+        phi1 = __dadd_rn(__dmul_rn(u_phi1, __dsub_rn(p.density_hi, p.density_lo)), p.density_lo);
+      } else if (p.density_kind == SS_DENSITY_INVCDF) {
+        phi1 = invcdf_phi1(a, itab, u_phi1);
+      } else if (p.density_kind == SS_DENSITY_GAUSSIAN) {  // u_phi1 slot carries a normal draw
+        double z = u_phi1;
+        if (!a.d.u_phi1) {
+          double ua, ub, z1;
+          ss::philox_pair(gi, SS_DRAW_BLOCK_DENSITY_Z, a.seed, ua, ub);
+          ss::box_muller(ua, ub, z, z1);
+        }
+        phi1 = __dadd_rn(__dmul_rn(z, p.density_hi), p.density_lo);
+      } else {
+        phi1 = ss::nan_d();
+      }
+
+      double n_phi2, n_dist;
+      if (a.d.n_phi2 && (a.d.n_dist || !p.has_dist)) {
+        n_phi2 = a.d.n_phi2[i];
+        n_dist = p.has_dist ? a.d.n_dist[i] : 0.0;
+      } else {
+        double ua, ub;
+        ss::philox_pair(gi, SS_DRAW_BLOCK_TRACK, a.seed, ua, ub);
+        const bool need_z = (p.track_sampler == SS_SAMPLER_GAUSSIAN) ||
+                            (p.has_dist && p.dist_sampler == SS_SAMPLER_GAUSSIAN);
+        double z0 = 0, z1 = 0;
+        if (need_z) ss::box_muller(ua, ub, z0, z1);
+        n_phi2 = (p.track_sampler == SS_SAMPLER_GAUSSIAN) ? z0 : ua;
+        n_dist = (p.dist_sampler == SS_SAMPLER_GAUSSIAN) ? z1 : ub;
+        if (a.d.n_phi2) n_phi2 = a.d.n_phi2[i];
+        if (a.d.n_dist) n_dist = a.d.n_dist[i];
+      }
+      const double phi2_given = a.in.phi2 ? a.in.phi2[i] : ss::nan_d();
+      phi2 = (phi2_given == phi2_given)
+                 ? phi2_given
+                 : track_sample(p.track_center, p.track_spread, p.track_sampler, tab, phi1, n_phi2, c_dom);
+      const double dist_given = a.in.dist ? a.in.dist[i] : ss::nan_d();
+      if (dist_given == dist_given) dist = dist_given;
+      if (p.has_dist || p.has_iso) {
+        if (!(dist_given == dist_given) && p.has_dist)
+          dist = track_sample(p.dist_center, p.dist_spread, p.dist_sampler, tab, phi1, n_dist, c_dom);
+        if (p.has_iso) {
+          double m1, m2;
+          iso_sample(p, tab, itab, u_mass, m1, m2, c_dom);
+          mag_g = __dadd_rn(m1, dist);
+          mag_r = __dadd_rn(m2, dist);
+        }
+      }
+      put<OutT>(a.o.phi1, i, phi1);
+      put<OutT>(a.o.phi2, i, phi2);
+      put<OutT>(a.o.dist, i, dist);
+      put<OutT>(a.o.mag[SS_BAND_G], i, mag_g);
+      put<OutT>(a.o.mag[SS_BAND_R], i, mag_r);
+    }
+
+    // ------------------------------------------------ rotate (observed.py:573)
+    if (ST & SS_STAGE_ROTATE) {
+      if (!(ST & SS_STAGE_GENERATE)) {
+        phi1 = a.in.phi1[i];
+        phi2 = a.in.phi2[i];
+      }
+      double sl, cl, sb, cb;
+      sincospi(phi1 * (1.0 / 180.0), &sl, &cl);
+      sincospi(phi2 * (1.0 / 180.0), &sb, &cb);
+      const double v0 = cb * cl, v1 = cb * sl, v2 = sb;
+      const double wx = p.R[0] * v0 + p.R[3] * v1 + p.R[6] * v2;
+      const double wy = p.R[1] * v0 + p.R[4] * v1 + p.R[7] * v2;
+      const double wz = p.R[2] * v0 + p.R[5] * v1 + p.R[8] * v2;
+      const double R2D = 57.29577951308232;
+      ra = atan2(wy, wx) * R2D;
+      if (ra < 0.0) ra += 360.0;
+      dec = atan2(wz, sqrt(wx * wx + wy * wy)) * R2D;
+      put<OutT>(a.o.ra, i, ra);
+      put<OutT>(a.o.dec, i, dec);
+    }
+
+    // ------------------------------------------------ observe (observed.py:146-291)
+    if (ST & SS_STAGE_OBSERVE) {
+      if (!(ST & SS_STAGE_ROTATE)) {
+        ra = a.in.ra[i];
+        dec = a.in.dec[i];
+      }
+      if (!(ST & SS_STAGE_GENERATE)) {
+        mag_g = p.band_present[SS_BAND_G] ? a.in.mag[SS_BAND_G][i] : ss::nan_d();
+        mag_r = p.band_present[SS_BAND_R] ? a.in.mag[SS_BAND_R][i] : ss::nan_d();
+      }
+      const ss::HpLoc L = ss::hp_locate(ra, dec);
+      double ebv = ss::nan_d(), ml_g = ss::nan_d(), ml_r = ss::nan_d();
+      if (L.valid) {
+        const long long pe = ss::hp_pix(L, p.nside_ebv, p.nest);
+        ebv = __ldg(&a.m.ebv[pe]);
+        long long pg = -1;
+        if (p.band_present[SS_BAND_G]) {
+          pg = (p.nside_maglim[SS_BAND_G] == p.nside_ebv) ? pe
+                                                          : ss::hp_pix(L, p.nside_maglim[SS_BAND_G], p.nest);
+          ml_g = __ldg(&a.m.maglim[SS_BAND_G][pg]);
+        }
+        if (p.band_present[SS_BAND_R]) {
+          const long long pr =
+              (p.nside_maglim[SS_BAND_R] == p.nside_ebv) ? pe
+              : (pg >= 0 && p.nside_maglim[SS_BAND_R] == p.nside_maglim[SS_BAND_G])
+                  ? pg
+                  : ss::hp_pix(L, p.nside_maglim[SS_BAND_R], p.nest);
+          ml_r = __ldg(&a.m.maglim[SS_BAND_R][pr]);
+        }
+        if (a.o.pix) a.o.pix[i] = ss::hp_pix(L, p.nside_pix, p.nest);
+      } else {
+        c_coord++;
+        if (a.o.pix) a.o.pix[i] = -1;
+      }
+
+      double z_g, z_r;
+      if (a.d.z_flux[SS_BAND_G] && a.d.z_flux[SS_BAND_R]) {
+        z_g = a.d.z_flux[SS_BAND_G][i];
+        z_r = a.d.z_flux[SS_BAND_R][i];
+      } else {
+        double ua, ub;
+        ss::philox_pair(gi, SS_DRAW_BLOCK_FLUX, a.seed, ua, ub);
+        ss::box_muller(ua, ub, z_r, z_g);
+        if (a.d.z_flux[SS_BAND_G]) z_g = a.d.z_flux[SS_BAND_G][i];
+        if (a.d.z_flux[SS_BAND_R]) z_r = a.d.z_flux[SS_BAND_R][i];
+      }
+      double u_det, u_det2;
+      if (a.d.u_det && (a.d.u_det2 || !p.perfect_galstarsep)) {
+        u_det = a.d.u_det[i];
+        u_det2 = p.perfect_galstarsep ? a.d.u_det2[i] : 0.0;
+      } else {
+        ss::philox_pair(gi, SS_DRAW_BLOCK_DETECT, a.seed, u_det, u_det2);
+        if (a.d.u_det) u_det = a.d.u_det[i];
+        if (a.d.u_det2) u_det2 = a.d.u_det2[i];
+      }
+
+      bool valid = true, flag_c = false, flag_d = false, snr_ok = true, snr_r_ok = true;
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        if (!p.band_present[b]) continue;
+        const double mag = b == SS_BAND_G ? mag_g : mag_r;
+        const double maglim = b == SS_BAND_G ? ml_g : ml_r;
+        const double zf = b == SS_BAND_G ? z_g : z_r;
+        const double ext = __dmul_rn(p.coeff_extinc[b], ebv);          // surveys.py:228
+        const double m_true = __dadd_rn(mag, ext);                     // observed.py:167
+        const double err = ss::photo_error(p, tab, b, m_true, maglim); // surveys.py:234-292
+        // sample_measured_magnitudes (observed.py:863-904, :984-1035)
+        const double flux = __dmul_rn(3631.0, exp10(__dmul_rn(-0.4, m_true)));
+        const double sig = __ddiv_rn(__dmul_rn(flux, err), 1.0857362);
+        const double fobs = __dadd_rn(flux, __dmul_rn(sig, zf));
+        const bool good = fobs > 0.0;
+        double mobs = ss::nan_d();
+        if (good) {
+          mobs = __dmul_rn(-2.5, log10(__ddiv_rn(fobs, 3631.0)));
+          if (p.dust_correction) mobs = __dsub_rn(mobs, ext);          // observed.py:194-208
+        }
+        valid = valid && good;
+        if (!good) { if (b == SS_BAND_G) c_bad_g++; else c_bad_r++; }
+        if (p.snr_cut[b]) snr_ok = snr_ok && (err <= p.snr_err_max);   // observed.py:266-281
+        if (b == SS_BAND_R) snr_r_ok = (err <= p.snr_err_max);         // observed.py:283-286
+        if (b == p.completeness_band) {                                // observed.py:224-243
+          flag_c = u_det <= ss::efficiency(p, p.completeness, tab, b, m_true, maglim);
+          if (p.perfect_galstarsep)
+            flag_d = u_det2 <= ss::efficiency(p, p.detection, tab, b, m_true, maglim);
+          if (maglim != maglim) c_unseen++;
+        }
+        put<OutT>(a.o.mag_obs[b], i, mobs);
+        put<OutT>(a.o.magerr[b], i, err);
+      }
+      const bool observed = valid && flag_c && snr_ok;
+      const bool perfect = p.perfect_galstarsep && valid && flag_d && snr_ok && snr_r_ok;
+      if (a.o.flag_observed) a.o.flag_observed[i] = observed ? 1 : 0;
+      if (a.o.flag_perfect) a.o.flag_perfect[i] = perfect ? 1 : 0;
+      c_obs += observed;
+      c_perf += perfect;
+    }
+
+    if (want_hist) {
+      const double hv[SS_N_HIST] = {phi1, phi2, dist, mag_g, mag_g - mag_r};
+#pragma unroll
+      for (int h = 0; h < SS_N_HIST; ++h) {
+        const double t = (hv[h] - p.hist_lo[h]) * p.hist_inv_width[h];
+        if (t >= 0.0 && t < (double)SS_HIST_BINS) atomicAdd(&s_hist[h * SS_HIST_BINS + (int)t], 1u);
+      }
+    }
+  }
+
+  if (want_cnt) {
+    const unsigned vals[8] = {c_tot, c_obs, c_perf, c_bad_g, c_bad_r, c_unseen, c_dom, c_coord};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const unsigned s = __reduce_add_sync(0xffffffffu, vals[k]);
+      if ((threadIdx.x & 31) == 0 && s) atomicAdd(&s_cnt[k], s);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < SS_N_COUNTERS; k += blockDim.x)
+      if (s_cnt[k]) atomicAdd(&a.o.counters[k], (unsigned long long)s_cnt[k]);
+    if (want_hist)
+      for (int k = threadIdx.x; k < SS_N_HIST * SS_HIST_BINS; k += blockDim.x)
+        if (s_hist[k]) atomicAdd(&a.o.counters[SS_N_COUNTERS + k], (unsigned long long)s_hist[k]);
+  }
+}
+
+// ---------------------------------------------------------------- small kernels
+__global__ void k_frame_fraction(SSParams p, SSMaps m, SSCatalog in, unsigned long long* counters,
+                                 unsigned long long n) {
+  unsigned inside = 0;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += stride) {
+    double sl, cl, sb, cb;
+    sincospi(in.phi1[i] * (1.0 / 180.0), &sl, &cl);
+    sincospi(in.phi2[i] * (1.0 / 180.0), &sb, &cb);
+    const double v0 = cb * cl, v1 = cb * sl, v2 = sb;
+    const double wx = p.R[0] * v0 + p.R[3] * v1 + p.R[6] * v2;
+    const double wy = p.R[1] * v0 + p.R[4] * v1 + p.R[7] * v2;
+    const double wz = p.R[2] * v0 + p.R[5] * v1 + p.R[8] * v2;
+    double ra = atan2(wy, wx) * 57.29577951308232;
+    if (ra < 0.0) ra += 360.0;
+    const double dec = atan2(wz, sqrt(wx * wx + wy * wy)) * 57.29577951308232;
+    const ss::HpLoc L = ss::hp_locate(ra, dec);
+    if (L.valid) inside += m.mask[ss::hp_pix(L, m.nside_mask, p.nest)] != 0;
+  }
+  const unsigned s = __reduce_add_sync(0xffffffffu, inside);
+  if ((threadIdx.x & 31) == 0 && s) atomicAdd(&counters[SS_CNT_INSIDE], (unsigned long long)s);
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&counters[SS_CNT_TOTAL], n);
+}
+
+__global__ void k_photo_error(SSParams p, const double* tab, int band, const double* mag,
+                              const double* maglim, double* out, unsigned long long n) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += stride)
+    out[i] = ss::photo_error(p, tab, band, mag[i], maglim[i]);
+}
+
+__global__ void k_efficiency(SSParams p, const double* tab, int band, int detection_only,
+                             const double* mag, const double* maglim, double* out,
+                             unsigned long long n) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += stride)
+    out[i] = ss::efficiency(p, detection_only ? p.detection : p.completeness, tab, band, mag[i],
+                            maglim[i]);
+}
+
+__global__ void k_eval_function(SSFunc f, const double* tab, const double* x, double* out,
+                                unsigned long long n) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += stride)
+    out[i] = ss::fn_eval(f, tab, x[i]);
+}
+
+__global__ void k_ang2pix(int nside, int nest, const double* lon, const double* lat,
+                          long long* pix, unsigned long long n) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += stride) {
+    const ss::HpLoc L = ss::hp_locate(lon[i], lat[i]);
+    pix[i] = L.valid ? ss::hp_pix(L, nside, nest) : -1;
+  }
+}
+
+// ---------------------------------------------------------------- host side
+struct DevInfo {
+  int device = -1, sms = 0, smem_optin = 0;
+};
+
+int device_info(DevInfo& d) {
+  SS_CUDA(cudaGetDevice(&d.device));
+  static thread_local DevInfo cache;
+  if (cache.device == d.device) { d = cache; return SS_OK; }
+  int major = 0;
+  SS_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d.device));
+  if (major != 10) return fail(SS_ENODEV, "device is not sm_100 (Blackwell B200)%s");
+  SS_CUDA(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, d.device));
+  SS_CUDA(cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d.device));
+  cache = d;
+  return SS_OK;
+}
+
+// static shared memory of k_stars (barrier + counters + histograms), rounded up
+constexpr int kStaticSmem = 8 + 4 * SS_N_COUNTERS + 4 * SS_N_HIST * SS_HIST_BINS + 256;
+
+int plan_launch(const DevInfo& d, int64_t blob_bytes, uint64_t n, int& smem, int& grid) {
+  smem = (blob_bytes > 0 && blob_bytes + kStaticSmem <= d.smem_optin) ? (int)blob_bytes : 0;
+  const uint64_t blocks_needed = (n + SS_BLOCK - 1) / SS_BLOCK;
+  // one persistent CTA per SM when the blob is large; otherwise as many as fit
+  int per_sm = 1;
+  if (smem + kStaticSmem <= d.smem_optin / 2) per_sm = 2;
+  const uint64_t cap = (uint64_t)d.sms * per_sm;
+  grid = (int)(blocks_needed < cap ? (blocks_needed ? blocks_needed : 1) : cap);
+  return SS_OK;
+}
+
+template <uint32_t ST, typename OutT>
+int launch_t(const KArgs& a, int smem, int grid, cudaStream_t stream) {
+  static thread_local int configured_smem = -1;
+  auto kern = k_stars<ST, OutT>;
+  if (smem > configured_smem) {
+    SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured_smem = smem;
+  }
+  kern<<<grid, SS_BLOCK, smem, stream>>>(a);
+  SS_CUDA(cudaGetLastError());
+  return SS_OK;
+}
+
+template <typename OutT>
+int launch_stage(uint32_t st, const KArgs& a, int smem, int grid, cudaStream_t s) {
+  switch (st) {
+    case 1: return launch_t<1, OutT>(a, smem, grid, s);
+    case 2: return launch_t<2, OutT>(a, smem, grid, s);
+    case 3: return launch_t<3, OutT>(a, smem, grid, s);
+    case 4: return launch_t<4, OutT>(a, smem, grid, s);
+    case 6: return launch_t<6, OutT>(a, smem, grid, s);
+    case 7: return launch_t<7, OutT>(a, smem, grid, s);
+  }
+  return fail(SS_EINVAL, "unsupported stage mask%s");
+}
+
+int check_func(const SSFunc& f, int64_t blob_doubles, const char* name) {
+  if (f.kind == SS_FN_LINEAR || f.kind == SS_FN_SPLINE || f.kind == SS_FN_SPLINE_PRODUCT) {
+    const int64_t need_c = f.kind == SS_FN_LINEAR ? 2LL * f.n : 4LL * (f.n - 1);
+    if (f.n < 2 || f.x_off < 0 || f.c_off < 0 || f.x_off + (int64_t)f.n > blob_doubles ||
+        f.c_off + need_c > blob_doubles)
+      return fail(SS_EINVAL, "function table '%s' lies outside the blob", name);
+  } else if (f.kind < SS_FN_NONE || f.kind > SS_FN_SPLINE_PRODUCT) {
+    return fail(SS_EINVAL, "unknown function kind in '%s'", name);
+  }
+  return SS_OK;
+}
+
+int validate(uint32_t st, const SSParams* p, const SSTables* t, const SSMaps* m,
+             const SSCatalog* in, const SSOut* out) {
+  if (!p || !out) return fail(SS_EINVAL, "params and out must not be NULL%s");
+  if (out->dtype != SS_DTYPE_F64 && out->dtype != SS_DTYPE_F32)
+    return fail(SS_EINVAL, "SSOut.dtype must be SS_DTYPE_F64 or SS_DTYPE_F32%s");
+  const int64_t nd = t ? t->blob_bytes / 8 : 0;
+  if (t && (t->blob_bytes % 16 != 0)) return fail(SS_EINVAL, "blob_bytes must be a multiple of 16%s");
+  if (st & SS_STAGE_GENERATE) {
+    if (!t) return fail(SS_EINVAL, "generate needs tables%s");
+    int rc;
+    if ((rc = check_func(p->track_center, nd, "track.center"))) return rc;
+    if ((rc = check_func(p->track_spread, nd, "track.spread"))) return rc;
+    if (p->track_center.kind == SS_FN_NONE || p->track_spread.kind == SS_FN_NONE)
+      return fail(SS_EINVAL, "track center/spread are required%s");
+    if (p->has_dist) {
+      if ((rc = check_func(p->dist_center, nd, "distance_modulus.center"))) return rc;
+      if ((rc = check_func(p->dist_spread, nd, "distance_modulus.spread"))) return rc;
+    }
+    if (p->density_kind == SS_DENSITY_INVCDF) {
+      if (!t->cdf_pairs || p->cdf_n < 2) return fail(SS_EINVAL, "inverse-CDF density needs cdf_pairs%s");
+      if (!p->cdf_identity && !t->cdf_perm) return fail(SS_EINVAL, "non-monotone CDF needs cdf_perm%s");
+      if (p->cdf_guide_n & (p->cdf_guide_n - 1)) return fail(SS_EINVAL, "cdf_guide_n must be a power of two%s");
+    }
+    if (p->has_iso) {
+      if (!p->has_dist && !(in && in->dist))
+        return fail(SS_EINVAL, "isochrone magnitudes need a distance modulus%s");
+      if (p->iso_n < 2 || p->imf_n < 2) return fail(SS_EINVAL, "isochrone/IMF tables too short%s");
+      if (p->imf_guide_n & (p->imf_guide_n - 1)) return fail(SS_EINVAL, "imf_guide_n must be a power of two%s");
+    }
+  }
+  if ((st & SS_STAGE_ROTATE) && !(st & SS_STAGE_GENERATE)) {
+    if (!in || !in->phi1 || !in->phi2) return fail(SS_EINVAL, "rotate needs catalog phi1/phi2%s");
+  }
+  if (st & SS_STAGE_OBSERVE) {
+    if (!t || !m) return fail(SS_EINVAL, "observe needs tables and maps%s");
+    if (!p->band_present[SS_BAND_R])
+      return fail(SS_EINVAL, "band 'r' is required (reference observed.py:256)%s");
+    if (!m->ebv) return fail(SS_EINVAL, "E(B-V) map not loaded%s");
+    for (int b = 0; b < 2; ++b)
+      if (p->band_present[b] && !m->maglim[b]) return fail(SS_EINVAL, "maglim map missing for a requested band%s");
+    if (!p->band_present[p->completeness_band & 1])
+      return fail(SS_EINVAL, "the completeness band must be in bands (reference observed.py:246-252)%s");
+    int rc;
+    if ((rc = check_func(p->photo_error, nd, "photo_error"))) return rc;
+    if ((rc = check_func(p->completeness, nd, "completeness"))) return rc;
+    if (p->photo_error.kind != SS_FN_LINEAR || p->completeness.kind != SS_FN_LINEAR)
+      return fail(SS_EINVAL, "photo_error/completeness must be SS_FN_LINEAR tables%s");
+    if (p->perfect_galstarsep) {
+      if ((rc = check_func(p->detection, nd, "detection"))) return rc;
+      if (p->detection.kind != SS_FN_LINEAR) return fail(SS_EINVAL, "detection table missing%s");
+    }
+    if (p->nest) {
+      const int ns[3] = {p->nside_ebv, p->nside_maglim[0], p->nside_maglim[1]};
+      for (int k = 0; k < 3; ++k)
+        if (ns[k] & (ns[k] - 1)) return fail(SS_EINVAL, "NESTED maps need power-of-two nside%s");
+    }
+    if (!(st & SS_STAGE_ROTATE) && (!in || !in->ra || !in->dec))
+      return fail(SS_EINVAL, "observe needs catalog ra/dec%s");
+    if (!(st & SS_STAGE_GENERATE)) {
+      if (!in) return fail(SS_EINVAL, "observe needs catalog magnitudes%s");
+      for (int b = 0; b < 2; ++b)
+        if (p->band_present[b] && !in->mag[b]) return fail(SS_EINVAL, "catalog magnitude column missing%s");
+    } else if (!p->has_iso) {
+      return fail(SS_EINVAL, "generate+observe needs an isochrone%s");
+    }
+  }
+  return SS_OK;
+}
+
+}  // namespace
+
+// ================================================================ C ABI
+extern "C" {
+
+int ss_abi_version(void) { return SS_ABI_VERSION; }
+const char* ss_last_error(void) { return g_err; }
+
+int ss_struct_sizes(int32_t* s) {
+  if (!s) return fail(SS_EINVAL, "sizes7 is NULL%s");
+  s[0] = sizeof(SSFunc); s[1] = sizeof(SSParams); s[2] = sizeof(SSTables); s[3] = sizeof(SSMaps);
+  s[4] = sizeof(SSCatalog); s[5] = sizeof(SSDraws); s[6] = sizeof(SSOut);
+  return SS_OK;
+}
+
+int ss_launch_info(int64_t blob_bytes, uint64_t n, int32_t* smem_bytes, int32_t* grid, int32_t* block) {
+  DevInfo d;
+  int rc = device_info(d);
+  if (rc) return rc;
+  int smem, g;
+  plan_launch(d, blob_bytes, n, smem, g);
+  if (smem_bytes) *smem_bytes = smem;
+  if (grid) *grid = g;
+  if (block) *block = SS_BLOCK;
+  return SS_OK;
+}
+
+int ss_run(uint32_t stages, const SSParams* p, const SSTables* t, const SSMaps* m,
+           const SSCatalog* in, const SSDraws* d, const SSOut* out, uint64_t n,
+           uint64_t star_offset, uint64_t seed, void* stream) {
+  int rc = validate(stages, p, t, m, in, out);
+  if (rc) return rc;
+  if (n == 0) return SS_OK;
+  DevInfo dev;
+  if ((rc = device_info(dev))) return rc;
+  KArgs a;
+  memset(&a, 0, sizeof(a));
+  a.p = *p;
+  if (t) a.t = *t;
+  if (m) a.m = *m;
+  if (in) a.in = *in;
+  if (d) a.d = *d;
+  a.o = *out;
+  a.n = n;
+  a.offset = star_offset;
+  a.seed = seed;
+  int smem, grid;
+  plan_launch(dev, a.t.blob_bytes, n, smem, grid);
+  a.blob_in_smem = smem > 0;
+  a.blob_bytes = (uint32_t)a.t.blob_bytes;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  return out->dtype == SS_DTYPE_F32 ? launch_stage<float>(stages, a, smem, grid, s)
+                                    : launch_stage<double>(stages, a, smem, grid, s);
+}
+
+int ss_generate(const SSParams* p, const SSTables* t, const SSDraws* d, const SSOut* out,
+                uint64_t n, uint64_t star_offset, uint64_t seed, void* stream) {
+  return ss_run(SS_STAGE_GENERATE, p, t, nullptr, nullptr, d, out, n, star_offset, seed, stream);
+}
+
+int ss_rotate(const SSParams* p, const SSCatalog* in, const SSOut* out, uint64_t n, void* stream) {
+  return ss_run(SS_STAGE_ROTATE, p, nullptr, nullptr, in, nullptr, out, n, 0, 0, stream);
+}
+
+int ss_observe(const SSParams* p, const SSTables* t, const SSMaps* m, const SSCatalog* in,
+               const SSDraws* d, const SSOut* out, uint64_t n, uint64_t star_offset,
+               uint64_t seed, void* stream) {
+  const uint32_t st = (in && in->ra && in->dec) ? SS_STAGE_OBSERVE
+                                                : (SS_STAGE_ROTATE | SS_STAGE_OBSERVE);
+  return ss_run(st, p, t, m, in, d, out, n, star_offset, seed, stream);
+}
+
+int ss_generate_observe(const SSParams* p, const SSTables* t, const SSMaps* m, const SSDraws* d,
+                        const SSOut* out, uint64_t n, uint64_t star_offset, uint64_t seed,
+                        void* stream) {
+  return ss_run(SS_STAGE_GENERATE | SS_STAGE_ROTATE | SS_STAGE_OBSERVE, p, t, m, nullptr, d, out,
+                n, star_offset, seed, stream);
+}
+
+static int small_grid(uint64_t n, int* grid) {
+  DevInfo d;
+  int rc = device_info(d);
+  if (rc) return rc;
+  const uint64_t need = (n + 255) / 256;
+  const uint64_t cap = (uint64_t)d.sms * 8;
+  *grid = (int)(need < cap ? (need ? need : 1) : cap);
+  return SS_OK;
+}
+
+int ss_frame_fraction(const SSParams* p, const SSMaps* m, const SSCatalog* in,
+                      unsigned long long* counters, uint64_t n, void* stream) {
+  if (!p || !m || !in || !counters || !m->mask || !in->phi1 || !in->phi2 || m->nside_mask < 1)
+    return fail(SS_EINVAL, "ss_frame_fraction: params, mask, phi1, phi2 and counters are required%s");
+  if (n == 0) return SS_OK;
+  int grid, rc;
+  if ((rc = small_grid(n, &grid))) return rc;
+  k_frame_fraction<<<grid, 256, 0, (cudaStream_t)stream>>>(*p, *m, *in, counters, n);
+  SS_CUDA(cudaGetLastError());
+  return SS_OK;
+}
+
+int ss_photo_error(const SSParams* p, const SSTables* t, int32_t band, const double* mag,
+                   const double* maglim, double* out, uint64_t n, void* stream) {
+  if (!p || !t || !t->blob || !mag || !maglim || !out || band < 0 || band > 1)
+    return fail(SS_EINVAL, "ss_photo_error: bad argument%s");
+  int rc = check_func(p->photo_error, t->blob_bytes / 8, "photo_error");
+  if (rc) return rc;
+  if (p->photo_error.kind != SS_FN_LINEAR) return fail(SS_EINVAL, "Photo error model not loaded%s");
+  if (n == 0) return SS_OK;
+  int grid;
+  if ((rc = small_grid(n, &grid))) return rc;
+  k_photo_error<<<grid, 256, 0, (cudaStream_t)stream>>>(*p, (const double*)t->blob, band, mag,
+                                                        maglim, out, n);
+  SS_CUDA(cudaGetLastError());
+  return SS_OK;
+}
+
+int ss_efficiency(const SSParams* p, const SSTables* t, int32_t band, int32_t detection_only,
+                  const double* mag, const double* maglim, double* out, uint64_t n, void* stream) {
+  if (!p || !t || !t->blob || !mag || !maglim || !out || band < 0 || band > 1)
+    return fail(SS_EINVAL, "ss_efficiency: bad argument%s");
+  const SSFunc& f = detection_only ? p->detection : p->completeness;
+  int rc = check_func(f, t->blob_bytes / 8, "efficiency");
+  if (rc) return rc;
+  if (f.kind != SS_FN_LINEAR) return fail(SS_EINVAL, "Efficiency function not loaded%s");
+  if (n == 0) return SS_OK;
+  int grid;
+  if ((rc = small_grid(n, &grid))) return rc;
+  k_efficiency<<<grid, 256, 0, (cudaStream_t)stream>>>(*p, (const double*)t->blob, band,
+                                                       detection_only, mag, maglim, out, n);
+  SS_CUDA(cudaGetLastError());
+  return SS_OK;
+}
+
+int ss_eval_function(const SSFunc* f, const SSTables* t, const double* x, double* out, uint64_t n,
+                     void* stream) {
+  if (!f || !x || !out) return fail(SS_EINVAL, "ss_eval_function: bad argument%s");
+  const bool tabular = f->kind >= SS_FN_LINEAR;
+  if (tabular && (!t || !t->blob)) return fail(SS_EINVAL, "ss_eval_function: table blob required%s");
+  int rc = check_func(*f, t ? t->blob_bytes / 8 : 0, "function");
+  if (rc) return rc;
+  if (n == 0) return SS_OK;
+  int grid;
+  if ((rc = small_grid(n, &grid))) return rc;
+  k_eval_function<<<grid, 256, 0, (cudaStream_t)stream>>>(*f, t ? (const double*)t->blob : nullptr,
+                                                          x, out, n);
+  SS_CUDA(cudaGetLastError());
+  return SS_OK;
+}
+
+int ss_ang2pix(int32_t nside, int32_t nest, const double* lon, const double* lat, int64_t* pix,
+               uint64_t n, void* stream) {
+  if (nside < 1 || !lon || !lat || !pix) return fail(SS_EINVAL, "ss_ang2pix: bad argument%s");
+  if (nest && (nside & (nside - 1))) return fail(SS_EINVAL, "NESTED needs power-of-two nside%s");
+  if (n == 0) return SS_OK;
+  int grid, rc;
+  if ((rc = small_grid(n, &grid))) return rc;
+  k_ang2pix<<<grid, 256, 0, (cudaStream_t)stream>>>(nside, nest, lon, lat, (long long*)pix, n);
+  SS_CUDA(cudaGetLastError());
+  return SS_OK;
+}
+
+// ---------------------------------------------------------------- host-buffer variants
+namespace {
+struct ColSpec { size_t off_out; int is_float; };  // float-typed column (dtype) or fixed type
+}
+
+static size_t elem_size(int32_t dtype) { return dtype == SS_DTYPE_F32 ? 4 : 8; }
+static uint64_t align256(uint64_t v) { return (v + 255) & ~255ULL; }
+
+// workspace layout per buffer (two buffers): 11 float columns, 2 flag columns, pix
+int64_t ss_host_workspace_bytes(uint64_t chunk, int32_t dtype) {
+  const uint64_t per = 11 * align256(chunk * elem_size(dtype)) + 2 * align256(chunk) +
+                       align256(chunk * 8) + 4 * align256(chunk * 8);
+  return (int64_t)(2 * per + align256(SS_COUNTERS_LEN * 8));
+}
+
+struct HostPipe {
+  cudaStream_t compute = nullptr, copy = nullptr;
+  cudaEvent_t done[2] = {nullptr, nullptr}, drained[2] = {nullptr, nullptr}, loaded[2] = {nullptr, nullptr};
+  int init() {
+    SS_CUDA(cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking));
+    SS_CUDA(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      SS_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+      SS_CUDA(cudaEventCreateWithFlags(&drained[i], cudaEventDisableTiming));
+      SS_CUDA(cudaEventCreateWithFlags(&loaded[i], cudaEventDisableTiming));
+    }
+    return SS_OK;
+  }
+  ~HostPipe() {
+    for (int i = 0; i < 2; ++i) {
+      if (done[i]) cudaEventDestroy(done[i]);
+      if (drained[i]) cudaEventDestroy(drained[i]);
+      if (loaded[i]) cudaEventDestroy(loaded[i]);
+    }
+    if (compute) cudaStreamDestroy(compute);
+    if (copy) cudaStreamDestroy(copy);
+  }
+};
+
+static int host_pipeline(uint32_t stages, const SSParams* p, const SSTables* t, const SSMaps* m,
+                         const SSCatalog* in_host, const SSOut* oh, uint64_t n,
+                         uint64_t star_offset, uint64_t seed, void* workspace,
+                         int64_t workspace_bytes, uint64_t chunk) {
+  if (!oh || !workspace) return fail(SS_EINVAL, "host variant: out and workspace are required%s");
+  if (chunk == 0) return fail(SS_EINVAL, "chunk must be > 0%s");
+  if (workspace_bytes < ss_host_workspace_bytes(chunk, oh->dtype))
+    return fail(SS_EINVAL, "workspace too small (see ss_host_workspace_bytes)%s");
+  const size_t es = elem_size(oh->dtype);
+  HostPipe pipe;
+  int rc = pipe.init();
+  if (rc) return rc;
+
+  // carve the workspace
+  char* base = (char*)workspace;
+  uint64_t cur = 0;
+  auto take = [&](uint64_t bytes) { char* q = base + cur; cur += align256(bytes); return (void*)q; };
+  SSOut dev[2];
+  SSCatalog cat[2];
+  void* const* host_cols[11] = {&oh->phi1, &oh->phi2, &oh->dist, &oh->mag[0], &oh->mag[1], &oh->ra,
+                                &oh->dec, &oh->mag_obs[0], &oh->mag_obs[1], &oh->magerr[0],
+                                &oh->magerr[1]};
+  for (int b = 0; b < 2; ++b) {
+    memset(&dev[b], 0, sizeof(SSOut));
+    memset(&cat[b], 0, sizeof(SSCatalog));
+    dev[b].dtype = oh->dtype;
+    void** dev_cols[11] = {&dev[b].phi1, &dev[b].phi2, &dev[b].dist, &dev[b].mag[0], &dev[b].mag[1],
+                           &dev[b].ra, &dev[b].dec, &dev[b].mag_obs[0], &dev[b].mag_obs[1],
+                           &dev[b].magerr[0], &dev[b].magerr[1]};
+    for (int c = 0; c < 11; ++c) {
+      void* q = take(chunk * es);
+      *dev_cols[c] = *host_cols[c] ? q : nullptr;
+    }
+    void* q = take(chunk); dev[b].flag_observed = oh->flag_observed ? (uint8_t*)q : nullptr;
+    q = take(chunk);       dev[b].flag_perfect = oh->flag_perfect ? (uint8_t*)q : nullptr;
+    q = take(chunk * 8);   dev[b].pix = oh->pix ? (int64_t*)q : nullptr;
+    // catalog staging (observe-only): ra, dec, mag_g, mag_r
+    cat[b].ra = (const double*)take(chunk * 8);
+    cat[b].dec = (const double*)take(chunk * 8);
+    cat[b].mag[0] = (const double*)take(chunk * 8);
+    cat[b].mag[1] = (const double*)take(chunk * 8);
+  }
+  unsigned long long* dcnt = (unsigned long long*)take(SS_COUNTERS_LEN * 8);
+  if (oh->counters) SS_CUDA(cudaMemsetAsync(dcnt, 0, SS_COUNTERS_LEN * 8, pipe.compute));
+
+  const bool has_cat = in_host != nullptr;
+  uint64_t k = 0;
+  for (uint64_t lo = 0; lo < n; lo += chunk, ++k) {
+    const int b = (int)(k & 1);
+    const uint64_t cn = (n - lo < chunk) ? (n - lo) : chunk;
+    // buffer b must have been drained by the copy stream two iterations ago
+    if (k >= 2) SS_CUDA(cudaStreamWaitEvent(pipe.compute, pipe.drained[b], 0));
+    SSCatalog cin;
+    memset(&cin, 0, sizeof(cin));
+    if (has_cat) {
+      // H2D of this chunk's catalog columns on the copy stream, ahead of the kernel
+      if (k >= 2) SS_CUDA(cudaStreamWaitEvent(pipe.copy, pipe.done[b], 0));
+      const double* hsrc[4] = {in_host->ra, in_host->dec, in_host->mag[0], in_host->mag[1]};
+      const double* ddst[4] = {cat[b].ra, cat[b].dec, cat[b].mag[0], cat[b].mag[1]};
+      const double** slot[4] = {&cin.ra, &cin.dec, &cin.mag[0], &cin.mag[1]};
+      for (int c = 0; c < 4; ++c) {
+        if (!hsrc[c]) continue;
+        SS_CUDA(cudaMemcpyAsync((void*)ddst[c], hsrc[c] + lo, cn * 8, cudaMemcpyHostToDevice, pipe.copy));
+        *slot[c] = ddst[c];
+      }
+      SS_CUDA(cudaEventRecord(pipe.loaded[b], pipe.copy));
+      SS_CUDA(cudaStreamWaitEvent(pipe.compute, pipe.loaded[b], 0));
+    }
+    SSOut o = dev[b];
+    o.counters = oh->counters ? dcnt : nullptr;
+    rc = ss_run(stages, p, t, m, has_cat ? &cin : nullptr, nullptr, &o, cn, star_offset + lo, seed,
+                pipe.compute);
+    if (rc) return rc;
+    SS_CUDA(cudaEventRecord(pipe.done[b], pipe.compute));
+    SS_CUDA(cudaStreamWaitEvent(pipe.copy, pipe.done[b], 0));
+    void* dcols[11] = {o.phi1, o.phi2, o.dist, o.mag[0], o.mag[1], o.ra, o.dec, o.mag_obs[0],
+                       o.mag_obs[1], o.magerr[0], o.magerr[1]};
+    for (int c = 0; c < 11; ++c)
+      if (dcols[c])
+        SS_CUDA(cudaMemcpyAsync((char*)*host_cols[c] + lo * es, dcols[c], cn * es,
+                                cudaMemcpyDeviceToHost, pipe.copy));
+    if (o.flag_observed)
+      SS_CUDA(cudaMemcpyAsync(oh->flag_observed + lo, o.flag_observed, cn, cudaMemcpyDeviceToHost, pipe.copy));
+    if (o.flag_perfect)
+      SS_CUDA(cudaMemcpyAsync(oh->flag_perfect + lo, o.flag_perfect, cn, cudaMemcpyDeviceToHost, pipe.copy));
+    if (o.pix)
+      SS_CUDA(cudaMemcpyAsync(oh->pix + lo, o.pix, cn * 8, cudaMemcpyDeviceToHost, pipe.copy));
+    SS_CUDA(cudaEventRecord(pipe.drained[b], pipe.copy));
+  }
+  SS_CUDA(cudaStreamSynchronize(pipe.compute));
+  if (oh->counters) {
+    unsigned long long tmp[SS_COUNTERS_LEN];
+    SS_CUDA(cudaMemcpyAsync(tmp, dcnt, sizeof(tmp), cudaMemcpyDeviceToHost, pipe.copy));
+    SS_CUDA(cudaStreamSynchronize(pipe.copy));
+    for (int i = 0; i < SS_COUNTERS_LEN; ++i) oh->counters[i] += tmp[i];
+  }
+  SS_CUDA(cudaStreamSynchronize(pipe.copy));
+  return SS_OK;
+}
+
+int ss_generate_observe_host(const SSParams* p, const SSTables* t, const SSMaps* m,
+                             const SSOut* out_host, uint64_t n, uint64_t star_offset,
+                             uint64_t seed, void* workspace, int64_t workspace_bytes,
+                             uint64_t chunk) {
+  return host_pipeline(SS_STAGE_GENERATE | SS_STAGE_ROTATE | SS_STAGE_OBSERVE, p, t, m, nullptr,
+                       out_host, n, star_offset, seed, workspace, workspace_bytes, chunk);
+}
+
+int ss_observe_host(const SSParams* p, const SSTables* t, const SSMaps* m,
+                    const SSCatalog* in_host, const SSOut* out_host, uint64_t n,
+                    uint64_t star_offset, uint64_t seed, void* workspace,
+                    int64_t workspace_bytes, uint64_t chunk) {
+  if (!in_host || !in_host->ra || !in_host->dec)
+    return fail(SS_EINVAL, "ss_observe_host needs host ra/dec columns%s");
+  return host_pipeline(SS_STAGE_OBSERVE, p, t, m, in_host, out_host, n, star_offset, seed,
+                       workspace, workspace_bytes, chunk);
+}
+
+}  // extern "C"

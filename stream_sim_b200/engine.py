@@ -1,0 +1,720 @@
+"""Host engine: packs lookup tables, owns device memory (PyTorch tensors) and
+launches the sm_100a kernels of libstreamsim_b200 through its C ABI.
+
+PyTorch is plumbing only (allocation, streams, ``torch.distributed``); every
+per-star number is produced by the hand-written CUDA library.  Nothing here
+falls back to NumPy: without the library or a B200 the calls raise.
+
+Layout in HBM (all fp64 unless noted):
+  * ``blob``      -- one packed buffer of small tables (knots, spline coefficients,
+                     isochrone rows, IMF CDF, efficiency / photo-error curves,
+                     int32 search guides); each CTA copies it to shared memory.
+  * ``cdf_pairs`` -- [100000][2] (sorted CDF value, slope) of the phi1 sampler.
+  * maps          -- dense RING HEALPix arrays, NaN = unseen (reference
+                     surveys.py:1272-1284), replicated on every GPU.
+  * outputs       -- structure of arrays, one contiguous column per quantity.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+
+COLUMNS_FLOAT = ("phi1", "phi2", "dist", "mag_g", "mag_r", "ra", "dec",
+                 "mag_g_obs", "mag_r_obs", "magerr_g", "magerr_r")
+GENERATE_COLUMNS = ("phi1", "phi2", "dist", "mag_g", "mag_r")
+ROTATE_COLUMNS = ("ra", "dec")
+OBSERVE_COLUMNS = ("mag_g_obs", "mag_r_obs", "magerr_g", "magerr_r", "flag_observed",
+                   "flag_perfect_galstarsep")
+SNR_MIN = 5.0            # reference observed.py:267
+CDF_GUIDE = 8192
+IMF_GUIDE = 2048
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def require_device(device=None):
+    """Return a torch CUDA device or raise: the product path has no CPU fallback."""
+    torch = _torch()
+    _lib.load()
+    if not torch.cuda.is_available():
+        raise _lib.StreamSimLibraryError(
+            "stream_sim_b200 needs an NVIDIA B200 (sm_100a) GPU; no CUDA device is visible "
+            "and there is no CPU fallback.")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise ValueError("device must be a CUDA device")
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device
+
+
+# ------------------------------------------------------------------ packing
+class BlobPacker:
+    """Accumulates the small tables of one launch configuration.
+
+    Doubles first, int32 guides after; offsets handed out for doubles are in
+    units of doubles from the blob start, int offsets are resolved by
+    :meth:`finalize` (they depend on the total size of the double region).
+    """
+
+    def __init__(self):
+        self._d = []
+        self._nd = 0
+        self._i = []
+        self._ni = 0
+        self._seen = {}
+
+    def add_doubles(self, arr, dedupe=False):
+        arr = np.ascontiguousarray(arr, dtype=np.float64).ravel()
+        key = arr.tobytes() if dedupe else None
+        if key is not None and key in self._seen:
+            return self._seen[key]
+        off = self._nd
+        self._d.append(arr)
+        self._nd += arr.size
+        if key is not None:
+            self._seen[key] = off
+        return off
+
+    def add_ints(self, arr):
+        arr = np.ascontiguousarray(arr, dtype=np.int32).ravel()
+        off = self._ni
+        self._i.append(arr)
+        self._ni += arr.size
+        return off
+
+    def add_linear(self, x, y):
+        """interp1d(kind='linear') tables: stable sort by x (scipy's
+        ``argsort(kind='mergesort')``), values, and np.interp's slopes."""
+        x = np.asarray(x, dtype=float)
+        y = np.asarray(y, dtype=float)
+        order = np.argsort(x, kind="mergesort")
+        xs, ys = x[order], y[order]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            slope = (ys[1:] - ys[:-1]) / (xs[1:] - xs[:-1])
+        x_off = self.add_doubles(xs, dedupe=True)
+        c_off = self.add_doubles(np.concatenate([ys, slope, [0.0]]))
+        return x_off, c_off, len(xs)
+
+    def add_spline(self, ppoly):
+        """scipy PPoly/CubicSpline: breakpoints and c[4, n-1] (highest power first)."""
+        x = np.asarray(ppoly.x, dtype=float)
+        c = np.asarray(ppoly.c, dtype=float)
+        assert c.shape == (4, len(x) - 1)
+        x_off = self.add_doubles(x, dedupe=True)
+        c_off = self.add_doubles(np.ascontiguousarray(c.T))
+        return x_off, c_off, len(x)
+
+    def finalize(self):
+        """-> (uint8 array, int_base): int offsets are ``int_base + local``."""
+        d = np.concatenate(self._d) if self._d else np.zeros(0)
+        if d.size % 2:
+            d = np.concatenate([d, [0.0]])
+        i = np.concatenate(self._i) if self._i else np.zeros(0, dtype=np.int32)
+        pad = (-i.size) % 4
+        i = np.concatenate([i, np.zeros(pad, dtype=np.int32)])
+        blob = np.concatenate([d.view(np.uint8), i.view(np.uint8)])
+        if blob.size == 0:
+            blob = np.zeros(16, dtype=np.uint8)
+        return blob, d.size * 2
+
+
+def search_guide(sorted_vals, guide_n):
+    """guide[g] = last index j with sorted_vals[j] <= g/guide_n (0 if none)."""
+    edges = np.arange(guide_n + 1, dtype=float) / guide_n
+    return np.maximum(np.searchsorted(sorted_vals, edges, side="right") - 1, 0).astype(np.int32)
+
+
+def snr_error_threshold(snr_min=SNR_MIN):
+    """Largest magerr e with fl(1/e) >= snr_min: turns the reference's
+    ``1.0/magerr >= 5.0`` (observed.py:278-279) into one compare, bit-exactly."""
+    e = 1.0 / snr_min
+    while 1.0 / np.nextafter(e, np.inf) >= snr_min:
+        e = np.nextafter(e, np.inf)
+    while not (1.0 / e >= snr_min):
+        e = np.nextafter(e, -np.inf)
+    return float(e)
+
+
+def frame_matrix(frame):
+    """3x3 ICRS->stream rotation from a GreatCircleFrame, ndarray or None."""
+    if frame is None:
+        return np.eye(3)
+    R = getattr(frame, "R", frame)
+    R = np.asarray(R, dtype=float)
+    if R.shape != (3, 3):
+        raise ValueError("frame must be a GreatCircleFrame or a 3x3 rotation matrix")
+    return R
+
+
+# ------------------------------------------------------------------ the engine
+class StarEngine:
+    """Device-resident configuration of one generate / rotate / observe pipeline.
+
+    Parameters
+    ----------
+    stream : stream_sim_b200.model.StreamModel or None
+        Needed for the generate stage.
+    survey : stream_sim_b200.surveys.Survey or None
+        Needed for the observe stage.
+    frame : GreatCircleFrame or 3x3 array, optional
+        Needed for the rotate stage.
+    bands, nside, dust_correction, perfect_galstarsep, detection_mag_cut :
+        ``StreamInjector.inject`` keywords (reference observed.py:95-131).
+    """
+
+    def __init__(self, stream=None, survey=None, frame=None, device=None, bands=("r", "g"),
+                 nside=4096, dust_correction=True, perfect_galstarsep=False,
+                 detection_mag_cut=("g",), nest=False, hist=None, cdf_steps=1e5):
+        torch = _torch()
+        self.lib = _lib.load()
+        self.device = require_device(device)
+        self.params = _lib.SSParams()
+        self.tables = _lib.SSTables()
+        self.maps = _lib.SSMaps()
+        self.has_generate = stream is not None
+        self.has_observe = survey is not None
+        self._keep = []                    # tensors referenced by raw pointers
+        packer = BlobPacker()
+        p = self.params
+        cdf_guide_local = imf_guide_local = None
+        if stream is not None:
+            cdf_guide_local, imf_guide_local = self._describe_stream(stream, packer, int(cdf_steps))
+        self.set_frame(frame)
+        if survey is not None:
+            self._describe_survey(survey, packer, bands, nside, dust_correction,
+                                  perfect_galstarsep, detection_mag_cut, nest)
+        self._describe_hist(hist)
+        blob, int_base = packer.finalize()
+        if cdf_guide_local is not None:
+            p.cdf_guide_off = int_base + cdf_guide_local
+        if imf_guide_local is not None:
+            p.imf_guide_off = int_base + imf_guide_local
+        self.blob = torch.from_numpy(blob).to(self.device)
+        self.tables.blob = self.blob.data_ptr()
+        self.tables.blob_bytes = self.blob.numel()
+
+    # ---- generate-side description (reference model.py:57-104, samplers.py)
+    def _describe_stream(self, stream, packer, cdf_steps):
+        from . import samplers as S
+        torch = _torch()
+        p = self.params
+        cdf_guide_local = imf_guide_local = None
+        dens = stream.density.density if stream.density is not None else None
+        if dens is None:
+            p.density_kind = _lib.DENSITY_NONE
+        elif isinstance(dens, S.UniformSampler):
+            p.density_kind = _lib.DENSITY_UNIFORM
+            p.density_lo, p.density_hi = float(dens.xmin), float(dens.xmax)
+        elif isinstance(dens, S.GaussianSampler):
+            p.density_kind = _lib.DENSITY_GAUSSIAN
+            p.density_lo, p.density_hi = float(dens.mu), float(dens.sigma)
+        elif isinstance(dens, S.InterpolationSampler):
+            p.density_kind = _lib.DENSITY_INVCDF
+            xg, pdf = dens.grid(cdf_steps)
+            cs, order = S.inverse_cdf_tables(xg, pdf)
+            self._set_cdf(xg, cs, order)
+            cdf_guide_local = packer.add_ints(search_guide(cs, CDF_GUIDE))
+            p.cdf_guide_n = CDF_GUIDE
+        else:
+            raise Exception(f"Unrecognized sampler: {type(dens).__name__}")
+
+        def sampler_kind(track):
+            kind = track._config.get("sampler", "Gaussian").lower()
+            if kind == "gaussian":
+                return _lib.SAMPLER_GAUSSIAN
+            if kind == "uniform":
+                return _lib.SAMPLER_UNIFORM
+            raise Exception(f"Unrecognized sampler: {kind}")
+
+        p.track_center = stream.track.center.describe(packer)
+        p.track_spread = stream.track.spread.describe(packer)
+        p.track_sampler = sampler_kind(stream.track)
+        if stream.distance_modulus is not None:
+            p.has_dist = 1
+            p.dist_center = stream.distance_modulus.center.describe(packer)
+            p.dist_spread = stream.distance_modulus.spread.describe(packer)
+            p.dist_sampler = sampler_kind(stream.distance_modulus)
+        iso = getattr(stream, "isochrone", None)
+        if iso is not None:
+            tab = iso.table
+            mg, mr = tab.mags_gr()
+            p.has_iso = 1
+            p.iso_n = len(tab.mass_init)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                dm = tab.mass_init[1:] - tab.mass_init[:-1]
+                sg = np.concatenate([(mg[1:] - mg[:-1]) / dm, [0.0]])
+                sr = np.concatenate([(mr[1:] - mr[:-1]) / dm, [0.0]])
+            p.iso_mass_off = packer.add_doubles(tab.mass_init)
+            p.iso_mag_off[_lib.BAND_G] = packer.add_doubles(mg)
+            p.iso_mag_off[_lib.BAND_R] = packer.add_doubles(mr)
+            p.iso_slope_off[_lib.BAND_G] = packer.add_doubles(sg)
+            p.iso_slope_off[_lib.BAND_R] = packer.add_doubles(sr)
+            n = len(tab.cdf)
+            lo, hi = float(tab.mass_grid[0]), float(tab.mass_grid[-1])
+            step = (hi - lo) / (n - 1)
+            ref = np.arange(n) * step + lo
+            ref[-1] = hi
+            if not np.array_equal(ref, tab.mass_grid):
+                raise AssertionError("IMF mass grid is not reproducible as lo + j*step")
+            p.imf_n, p.imf_mass_lo, p.imf_mass_hi, p.imf_mass_step = n, lo, hi, step
+            p.imf_cdf_off = packer.add_doubles(tab.cdf)
+            imf_guide_local = packer.add_ints(search_guide(tab.cdf, IMF_GUIDE))
+            p.imf_guide_n = IMF_GUIDE
+        return cdf_guide_local, imf_guide_local
+
+    def _set_cdf(self, xg, cs, order):
+        """Upload the phi1 inverse-CDF tables (reference samplers.py:69-76)."""
+        torch = _torch()
+        p = self.params
+        n = len(cs)
+        perm = order.astype(float)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            slope = np.concatenate([(perm[1:] - perm[:-1]) / (cs[1:] - cs[:-1]), [0.0]])
+        pairs = np.ascontiguousarray(np.stack([cs, slope], axis=1))
+        self.cdf_pairs = torch.from_numpy(pairs).to(self.device)
+        self.tables.cdf_pairs = self.cdf_pairs.data_ptr()
+        p.cdf_n = n
+        p.cdf_first, p.cdf_last = float(cs[0]), float(cs[-1])
+        p.cdf_identity = int(np.array_equal(order, np.arange(n)))
+        if not p.cdf_identity:
+            self.cdf_perm = torch.from_numpy(order.astype(np.int32)).to(self.device)
+            self.tables.cdf_perm = self.cdf_perm.data_ptr()
+        lo, hi = float(xg[0]), float(xg[-1])
+        step = (hi - lo) / (n - 1)
+        ref = np.arange(n) * step + lo
+        ref[-1] = hi
+        p.density_lo, p.density_hi, p.grid_step = lo, hi, step
+        if not np.array_equal(ref, xg):      # arbitrary `vals`: ship the grid itself
+            self.grid = torch.from_numpy(np.ascontiguousarray(xg, dtype=float)).to(self.device)
+            self.tables.grid = self.grid.data_ptr()
+
+    # ---- rotate
+    def set_frame(self, frame):
+        R = frame_matrix(frame)
+        for k in range(9):
+            self.params.R[k] = float(R.flat[k])
+        self.frame = frame
+
+    # ---- observe-side description (reference surveys.py getters, observed.py:146-291)
+    def _describe_survey(self, survey, packer, bands, nside, dust_correction,
+                         perfect_galstarsep, detection_mag_cut, nest):
+        torch = _torch()
+        from .healpix import npix2nside
+        p = self.params
+        for band in bands:
+            if band not in ("r", "g"):
+                raise ValueError("Currently only 'r' and 'g' bands are supported.")
+        cb = survey.completeness_band
+        if cb not in bands:
+            raise ValueError(f"Detection flag requires '{cb}' band to be in bands.")
+        if survey.ebv_map is None:
+            raise ValueError("E(B-V) map not loaded")
+        if survey.log_photo_error is None:
+            raise ValueError("Photo error model not loaded")
+        if survey.completeness is None:
+            raise ValueError("Efficiency function for type 'completeness' not loaded")
+        self.bands = tuple(bands)
+        p.nside_pix = int(nside)
+        p.nest = int(bool(nest))
+        p.dust_correction = int(bool(dust_correction))
+        p.perfect_galstarsep = int(bool(perfect_galstarsep))
+        p.completeness_band = _lib.BAND_INDEX[cb]
+        p.delta_saturation = float(survey.delta_saturation)
+        p.snr_err_max = snr_error_threshold(SNR_MIN)
+
+        def device_map(arr):
+            if isinstance(arr, torch.Tensor):
+                t = arr.to(device=self.device, dtype=torch.float64).contiguous()
+            else:
+                t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64)).to(self.device)
+            self._keep.append(t)
+            return t
+
+        ebv = device_map(survey.ebv_map)
+        p.nside_ebv = npix2nside(ebv.numel())
+        self.maps.ebv = ebv.data_ptr()
+        for band in ("g", "r"):
+            b = _lib.BAND_INDEX[band]
+            if band not in bands:
+                continue
+            if band not in survey.maglim_maps or survey.maglim_maps[band] is None:
+                raise ValueError(f"Band '{band}' not available. Available: {survey.bands}")
+            if band not in survey.coeff_extinc:
+                raise ValueError(f"Band '{band}' not available. Available: {survey.bands}")
+            ml = device_map(survey.maglim_maps[band])
+            p.band_present[b] = 1
+            p.nside_maglim[b] = npix2nside(ml.numel())
+            self.maps.maglim[b] = ml.data_ptr()
+            p.coeff_extinc[b] = float(survey.coeff_extinc[band])
+            p.saturation[b] = float(survey.saturation[band])
+            p.sys_error[b] = float(survey.sys_error.get(band, 0.005))
+            p.snr_cut[b] = int(band in detection_mag_cut)
+        from .surveys import TabulatedFunction
+        pe = TabulatedFunction.coerce(survey.log_photo_error)
+        p.photo_error = pe.describe(packer)
+        dsat = survey.delta_saturation
+        p.log_err_at_dsat = float(pe(dsat))
+        p.err_bright = float(10 ** pe(dsat - 1))
+        p.completeness = TabulatedFunction.coerce(survey.completeness).describe(packer)
+        if perfect_galstarsep:
+            det = getattr(survey, "efficiency_detection", None)
+            if det is None:
+                raise ValueError("Efficiency function for type 'detection_efficiency' not loaded")
+            p.detection = TabulatedFunction.coerce(det).describe(packer)
+
+    def _describe_hist(self, hist):
+        p = self.params
+        ranges = dict(phi1=(-20.0, 20.0), phi2=(-5.0, 5.0), dist=(10.0, 25.0),
+                      mag_g=(10.0, 35.0), g_minus_r=(-0.5, 2.5))
+        if hist:
+            ranges.update(hist if isinstance(hist, dict) else {})
+        p.hist_enable = int(bool(hist))
+        for k, name in enumerate(_lib.HIST_NAMES):
+            lo, hi = ranges[name]
+            p.hist_lo[k] = lo
+            p.hist_inv_width[k] = _lib.HIST_BINS / (hi - lo)
+        self.hist_ranges = ranges
+
+    # ---- launches
+    def _stream_ptr(self):
+        return C.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+
+    def new_counters(self):
+        return _torch().zeros(_lib.COUNTERS_LEN, dtype=_torch().int64, device=self.device)
+
+    def allocate(self, n, columns, dtype="f64", pix=False):
+        """Structure-of-arrays output buffers for ``columns``."""
+        torch = _torch()
+        ft = torch.float64 if dtype == "f64" else torch.float32
+        out = {}
+        for c in columns:
+            if c in COLUMNS_FLOAT:
+                out[c] = torch.empty(n, dtype=ft, device=self.device)
+            elif c in ("flag_observed", "flag_perfect_galstarsep"):
+                out[c] = torch.empty(n, dtype=torch.uint8, device=self.device)
+        if pix:
+            out["pix"] = torch.empty(n, dtype=torch.int64, device=self.device)
+        return out
+
+    def _out_struct(self, out, counters, dtype):
+        o = _lib.SSOut()
+        o.dtype = _lib.DTYPE_F64 if dtype == "f64" else _lib.DTYPE_F32
+        ptr = lambda k: out[k].data_ptr() if k in out and out[k] is not None else None
+        o.phi1, o.phi2, o.dist = ptr("phi1"), ptr("phi2"), ptr("dist")
+        o.mag[_lib.BAND_G], o.mag[_lib.BAND_R] = ptr("mag_g"), ptr("mag_r")
+        o.ra, o.dec = ptr("ra"), ptr("dec")
+        o.mag_obs[_lib.BAND_G], o.mag_obs[_lib.BAND_R] = ptr("mag_g_obs"), ptr("mag_r_obs")
+        o.magerr[_lib.BAND_G], o.magerr[_lib.BAND_R] = ptr("magerr_g"), ptr("magerr_r")
+        o.flag_observed = ptr("flag_observed")
+        o.flag_perfect = ptr("flag_perfect_galstarsep")
+        o.pix = ptr("pix")
+        o.counters = counters.data_ptr() if counters is not None else None
+        return o
+
+    def _as_device_f64(self, arr):
+        torch = _torch()
+        if arr is None:
+            return None
+        if isinstance(arr, torch.Tensor):
+            t = arr.to(device=self.device, dtype=torch.float64).contiguous()
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64)).to(self.device)
+        return t
+
+    def _draws_struct(self, draws, hold):
+        d = _lib.SSDraws()
+        if not draws:
+            return d
+
+        def get(*names):
+            for nm in names:
+                if nm in draws and draws[nm] is not None:
+                    t = self._as_device_f64(draws[nm])
+                    hold.append(t)
+                    return t.data_ptr()
+            return None
+        p = self.params
+        d.u_phi1 = get("z_phi1") if p.density_kind == _lib.DENSITY_GAUSSIAN else get("u_phi1")
+        d.n_phi2 = get("z_phi2") if p.track_sampler == _lib.SAMPLER_GAUSSIAN else get("u_phi2")
+        d.n_dist = get("z_dist") if p.dist_sampler == _lib.SAMPLER_GAUSSIAN else get("u_dist")
+        d.u_mass = get("u_mass")
+        d.z_flux[_lib.BAND_G], d.z_flux[_lib.BAND_R] = get("z_g"), get("z_r")
+        d.u_det, d.u_det2 = get("u_det"), get("u_det2")
+        return d
+
+    def run(self, stages, n, out, catalog=None, draws=None, seed=0, offset=0, counters=None,
+            dtype="f64"):
+        """Launch ``stages`` for ``n`` stars into the column tensors of ``out``."""
+        hold = []
+        cat = _lib.SSCatalog()
+        if catalog:
+            for name in ("phi1", "phi2", "dist", "ra", "dec"):
+                if catalog.get(name) is not None:
+                    t = self._as_device_f64(catalog[name])
+                    hold.append(t)
+                    setattr(cat, name, t.data_ptr())
+            for band in ("g", "r"):
+                if catalog.get("mag_" + band) is not None:
+                    t = self._as_device_f64(catalog["mag_" + band])
+                    hold.append(t)
+                    cat.mag[_lib.BAND_INDEX[band]] = t.data_ptr()
+        d = self._draws_struct(draws, hold)
+        o = self._out_struct(out, counters, dtype)
+        with _torch().cuda.device(self.device):
+            rc = self.lib.ss_run(stages, C.byref(self.params), C.byref(self.tables),
+                                 C.byref(self.maps), C.byref(cat), C.byref(d), C.byref(o),
+                                 int(n), int(offset), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                 self._stream_ptr())
+        _lib.check(rc)
+        # tensors in `hold` are only read by work already queued on the current stream;
+        # the caching allocator reuses their memory in stream order, so dropping them is safe
+        return out
+
+    def generate(self, n, seed=0, offset=0, draws=None, counters=None, dtype="f64", out=None):
+        cols = [c for c in GENERATE_COLUMNS
+                if not (c == "dist" and not self.params.has_dist)
+                and not (c.startswith("mag_") and not self.params.has_iso)]
+        out = out if out is not None else self.allocate(n, cols, dtype)
+        return self.run(_lib.STAGE_GENERATE, n, out, None, draws, seed, offset, counters, dtype)
+
+    def rotate(self, phi1, phi2, counters=None, dtype="f64", out=None):
+        n = len(phi1)
+        out = out if out is not None else self.allocate(n, ROTATE_COLUMNS, dtype)
+        return self.run(_lib.STAGE_ROTATE, n, out, dict(phi1=phi1, phi2=phi2), None, 0, 0,
+                        counters, dtype)
+
+    def _observe_columns(self, pix):
+        cols = []
+        for b in ("g", "r"):
+            if self.params.band_present[_lib.BAND_INDEX[b]]:
+                cols += [f"mag_{b}_obs", f"magerr_{b}"]
+        cols.append("flag_observed")
+        if self.params.perfect_galstarsep:
+            cols.append("flag_perfect_galstarsep")
+        return cols
+
+    def observe(self, catalog, seed=0, offset=0, draws=None, counters=None, dtype="f64",
+                out=None, pix=False):
+        """catalog: dict with (ra, dec) or (phi1, phi2), and mag_g / mag_r."""
+        has_radec = catalog.get("ra") is not None and catalog.get("dec") is not None
+        n = len(catalog["ra"] if has_radec else catalog["phi1"])
+        stages = _lib.STAGE_OBSERVE if has_radec else (_lib.STAGE_ROTATE | _lib.STAGE_OBSERVE)
+        cols = self._observe_columns(pix) + ([] if has_radec else list(ROTATE_COLUMNS))
+        out = out if out is not None else self.allocate(n, cols, dtype, pix=pix)
+        return self.run(stages, n, out, catalog, draws, seed, offset, counters, dtype)
+
+    def generate_observe(self, n, seed=0, offset=0, draws=None, counters=None, dtype="f64",
+                         out=None, pix=False, columns=None):
+        if out is None:
+            cols = columns if columns is not None else (
+                list(GENERATE_COLUMNS) + list(ROTATE_COLUMNS) + self._observe_columns(pix))
+            out = self.allocate(n, cols, dtype, pix=pix)
+        st = _lib.STAGE_GENERATE | _lib.STAGE_ROTATE | _lib.STAGE_OBSERVE
+        return self.run(st, n, out, None, draws, seed, offset, counters, dtype)
+
+    # ---- host-buffer entry (pinned host memory in, pinned host memory out)
+    def host_workspace(self, chunk, dtype="f64"):
+        torch = _torch()
+        nbytes = self.lib.ss_host_workspace_bytes(int(chunk),
+                                                  _lib.DTYPE_F64 if dtype == "f64" else _lib.DTYPE_F32)
+        return torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+
+    def allocate_host(self, n, columns, dtype="f64", pix=False, counters=True):
+        """Pinned host column buffers for the *_host entry points."""
+        torch = _torch()
+        ft = torch.float64 if dtype == "f64" else torch.float32
+        out = {}
+        for c in columns:
+            if c in COLUMNS_FLOAT:
+                out[c] = torch.empty(n, dtype=ft).pin_memory()
+            elif c in ("flag_observed", "flag_perfect_galstarsep"):
+                out[c] = torch.empty(n, dtype=torch.uint8).pin_memory()
+        if pix:
+            out["pix"] = torch.empty(n, dtype=torch.int64).pin_memory()
+        if counters:
+            out["counters"] = torch.zeros(_lib.COUNTERS_LEN, dtype=torch.int64).pin_memory()
+        return out
+
+    def generate_observe_host(self, n, out_host, workspace, chunk, seed=0, offset=0, dtype="f64"):
+        o = self._out_struct(out_host, out_host.get("counters"), dtype)
+        with _torch().cuda.device(self.device):
+            rc = self.lib.ss_generate_observe_host(
+                C.byref(self.params), C.byref(self.tables), C.byref(self.maps), C.byref(o),
+                int(n), int(offset), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                C.c_void_p(workspace.data_ptr()), workspace.numel(), int(chunk))
+        _lib.check(rc)
+        return out_host
+
+    def observe_host(self, catalog_host, out_host, workspace, chunk, seed=0, offset=0,
+                     dtype="f64"):
+        """catalog_host: dict of (pinned) CPU float64 tensors ra, dec, mag_g, mag_r."""
+        cat = _lib.SSCatalog()
+        cat.ra, cat.dec = catalog_host["ra"].data_ptr(), catalog_host["dec"].data_ptr()
+        for band in ("g", "r"):
+            if catalog_host.get("mag_" + band) is not None:
+                cat.mag[_lib.BAND_INDEX[band]] = catalog_host["mag_" + band].data_ptr()
+        n = catalog_host["ra"].numel()
+        o = self._out_struct(out_host, out_host.get("counters"), dtype)
+        with _torch().cuda.device(self.device):
+            rc = self.lib.ss_observe_host(
+                C.byref(self.params), C.byref(self.tables), C.byref(self.maps), C.byref(cat),
+                C.byref(o), int(n), int(offset), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                C.c_void_p(workspace.data_ptr()), workspace.numel(), int(chunk))
+        _lib.check(rc)
+        return out_host
+
+    # ---- summaries
+    @staticmethod
+    def summarize(counters):
+        """Counter tensor -> dict (one device->host copy)."""
+        c = counters.detach().cpu().numpy().astype(np.int64)
+        names = ("n_total", "n_observed", "n_perfect_galstarsep", "n_badmag_g", "n_badmag_r",
+                 "n_unseen", "n_domain_error", "n_bad_coord", "n_inside_mask")
+        out = {k: int(c[i]) for i, k in enumerate(names)}
+        for h, name in enumerate(_lib.HIST_NAMES):
+            lo = _lib.N_COUNTERS + h * _lib.HIST_BINS
+            out["hist_" + name] = c[lo:lo + _lib.HIST_BINS].copy()
+        return out
+
+    @staticmethod
+    def raise_for_counters(summary):
+        """Re-raise, after the fact, what SciPy / healpy would have raised per call."""
+        if summary["n_domain_error"]:
+            raise ValueError("Domain error in arguments. The `scale` parameter must be positive "
+                             "for all distributions, and many distributions have restrictions "
+                             "on shape parameters. (%d stars)" % summary["n_domain_error"])
+        if summary["n_bad_coord"]:
+            raise ValueError("THETA is out of range [0,pi] (%d stars)" % summary["n_bad_coord"])
+
+
+# ------------------------------------------------------------------ small ops
+def _small_call(fn, device, *args):
+    torch = _torch()
+    with torch.cuda.device(device):
+        rc = fn(*args, C.c_void_p(torch.cuda.current_stream(device).cuda_stream))
+    _lib.check(rc)
+
+
+def ang2pix(nside, lon, lat, nest=False, device=None):
+    """HEALPix pixel of (lon, lat) in degrees -- ``healpy.ang2pix(..., lonlat=True)``.
+    Returns an int64 torch tensor on the device."""
+    torch = _torch()
+    device = require_device(device)
+    lib = _lib.load()
+    to = lambda a: (a.to(device=device, dtype=torch.float64).contiguous()
+                    if isinstance(a, torch.Tensor)
+                    else torch.from_numpy(np.ascontiguousarray(np.atleast_1d(a), dtype=np.float64)).to(device))
+    lon_t, lat_t = to(lon), to(lat)
+    pix = torch.empty(lon_t.numel(), dtype=torch.int64, device=device)
+    _small_call(lib.ss_ang2pix, device, int(nside), int(bool(nest)), lon_t.data_ptr(),
+                lat_t.data_ptr(), pix.data_ptr(), lon_t.numel())
+    return pix
+
+
+def sample_inverse_cdf(vals, pdf, size, seed=None, u=None, device=None):
+    """GPU implementation of ``inverse_transform_sample`` (reference samplers.py:55-76)."""
+    from .samplers import inverse_cdf_tables
+    torch = _torch()
+    eng = StarEngine.__new__(StarEngine)
+    eng.lib = _lib.load()
+    eng.device = require_device(device)
+    eng.params, eng.tables, eng.maps = _lib.SSParams(), _lib.SSTables(), _lib.SSMaps()
+    eng._keep = []
+    p = eng.params
+    cs, order = inverse_cdf_tables(vals, pdf)
+    p.density_kind = _lib.DENSITY_INVCDF
+    eng._set_cdf(vals, cs, order)
+    packer = BlobPacker()
+    local = packer.add_ints(search_guide(cs, CDF_GUIDE))
+    p.cdf_guide_n = CDF_GUIDE
+    p.track_center.kind = p.track_spread.kind = _lib.FN_CONSTANT
+    p.track_center.xmin = p.track_spread.xmin = -np.inf
+    p.track_center.xmax = p.track_spread.xmax = np.inf
+    blob, int_base = packer.finalize()
+    p.cdf_guide_off = int_base + local
+    eng.blob = torch.from_numpy(blob).to(eng.device)
+    eng.tables.blob, eng.tables.blob_bytes = eng.blob.data_ptr(), eng.blob.numel()
+    eng.set_frame(None)
+    eng._describe_hist(None)
+    out = eng.allocate(size, ["phi1"])
+    seed = _fresh_seed() if seed is None else seed
+    eng.run(_lib.STAGE_GENERATE, size, out, None, dict(u_phi1=u) if u is not None else None, seed)
+    return out["phi1"].cpu().numpy()
+
+
+def sample_loc_scale(loc, scale, size, normal, seed=None, draws=None, device=None):
+    """``draw * scale + loc`` per star on the GPU (scipy ``rv.rvs`` semantics,
+    reference samplers.py:101-102), scalar or per-star loc/scale.
+
+    Implemented with the generate stage: an identity phi1 channel carries the
+    star index, the track channel applies the location/scale."""
+    torch = _torch()
+    device = require_device(device)
+    size = int(size)
+    loc_a = np.broadcast_to(np.asarray(loc, dtype=float), (size,))
+    scale_a = np.broadcast_to(np.asarray(scale, dtype=float), (size,))
+    if not np.all(scale_a >= 0):
+        raise ValueError("Domain error in arguments. The `scale` parameter must be positive for "
+                         "all distributions, and many distributions have restrictions on shape "
+                         "parameters.")
+    seed = _fresh_seed() if seed is None else seed
+    unit = _unit_engine(device, normal)
+    out = unit.allocate(size, ["phi2"])
+    d = None
+    if draws is not None:
+        d = {("z_phi2" if normal else "u_phi2"): draws}
+    unit.run(_lib.STAGE_GENERATE, size, out, None, d, seed)
+    z = out["phi2"]
+    res = z * torch.from_numpy(np.ascontiguousarray(scale_a)).to(device) \
+        + torch.from_numpy(np.ascontiguousarray(loc_a)).to(device)
+    return res.cpu().numpy()
+
+
+_UNIT = {}
+
+
+def _unit_engine(device, normal):
+    """Engine whose phi2 column is a raw standard draw (centre 0, scale 1)."""
+    key = (str(device), bool(normal))
+    if key in _UNIT:
+        return _UNIT[key]
+    torch = _torch()
+    eng = StarEngine.__new__(StarEngine)
+    eng.lib = _lib.load()
+    eng.device = device
+    eng.params, eng.tables, eng.maps = _lib.SSParams(), _lib.SSTables(), _lib.SSMaps()
+    eng._keep = []
+    p = eng.params
+    p.density_kind = _lib.DENSITY_UNIFORM
+    p.density_lo, p.density_hi = 0.0, 1.0
+    for f, v in ((p.track_center, 0.0), (p.track_spread, 1.0)):
+        f.kind, f.xmin, f.xmax = _lib.FN_CONSTANT, -np.inf, np.inf
+        f.p[0] = v
+    if normal:
+        p.track_sampler = _lib.SAMPLER_GAUSSIAN
+    else:
+        # Uniform sampler on [c-s, c+s] with c=s=0.5 -> u*1 + 0
+        p.track_sampler = _lib.SAMPLER_UNIFORM
+        p.track_center.p[0] = 0.5
+        p.track_spread.p[0] = 0.5
+    blob, _ = BlobPacker().finalize()
+    eng.blob = torch.from_numpy(blob).to(device)
+    eng.tables.blob, eng.tables.blob_bytes = eng.blob.data_ptr(), eng.blob.numel()
+    eng.set_frame(None)
+    eng._describe_hist(None)
+    _UNIT[key] = eng
+    return eng
+
+
+def _fresh_seed():
+    return int.from_bytes(os.urandom(8), "little")
