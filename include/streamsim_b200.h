@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SS_ABI_VERSION 3
+#define SS_ABI_VERSION 4
 
 /* error codes */
 #define SS_OK 0
@@ -115,7 +115,12 @@ typedef struct SSFunc {
   int32_t c_off;  /* LINEAR: y[n] then slope[n]; SPLINE: c[4*(n-1)], highest power first */
   double xmin, xmax; /* result is NaN outside [xmin,xmax] */
   double p[4];
-  int32_t n2, x2_off, c2_off, pad_; /* second spline of SS_FN_SPLINE_PRODUCT */
+  int32_t n2, x2_off, c2_off; /* second spline of SS_FN_SPLINE_PRODUCT */
+  /* optional uniform-bucket search guide over x[] (LINEAR tables): int32 guide[g_n]
+   * stored inside the double blob at g_off (in doubles); bucket = (x-g_x0)*g_inv */
+  int32_t g_n;
+  int32_t g_off, pad_;
+  double g_x0, g_inv;
 } SSFunc;
 
 typedef struct SSParams {
@@ -133,14 +138,16 @@ typedef struct SSParams {
   int32_t has_dist, has_iso;
   /* ---- generate: isochrone (model.py:575-604; ugali imf.sample + interp1d) */
   int32_t iso_n;        /* rows of (mass_init, mag_1, mag_2), sorted by mass      */
-  int32_t iso_mass_off, iso_mag_off[2], iso_slope_off[2]; /* blob offsets, doubles */
+  int32_t iso_mass_off, iso_mag_off[2]; /* blob offsets (doubles); mag[n] then slope[n] */
+  int32_t iso_guide_n, iso_guide_off;   /* uniform-bucket guide over mass_init     */
   int32_t imf_n;        /* IMF CDF steps (ugali: 10000)                           */
   int32_t imf_cdf_off;  /* blob offset of cdf[imf_n]                              */
   int32_t imf_guide_n;  /* power of two                                           */
-  int32_t imf_guide_off;/* blob offset IN INT32 UNITS of guide[imf_guide_n+1]     */
-  int32_t cdf_guide_off;/* blob offset IN INT32 UNITS of guide[cdf_guide_n+1]     */
+  int32_t imf_guide_off;/* blob offset (in doubles) of int32 guide[imf_guide_n+1] */
+  int32_t cdf_guide_off;/* blob offset (in doubles) of int32 guide[cdf_guide_n+1] */
   int32_t pad0_;
   double imf_mass_lo, imf_mass_hi, imf_mass_step; /* np.linspace(lo,hi,imf_n)     */
+  double iso_guide_x0, iso_guide_inv;
   /* ---- rotate: R rows = (origin, pole x origin, pole), ICRS -> stream frame */
   double R[9];
   /* ---- observe */
@@ -166,7 +173,7 @@ typedef struct SSParams {
 } SSParams;
 
 typedef struct SSTables {
-  const void* blob;          /* packed small tables (doubles first, int32 guides after) */
+  const void* blob;          /* packed small tables (doubles; int32 guides embedded)    */
   int64_t blob_bytes;        /* multiple of 16                                    */
   const double* cdf_pairs;   /* [cdf_n][2] = (sorted cdf_j, slope_j)              */
   const int32_t* cdf_perm;   /* [cdf_n] original index of sorted entry j; NULL if identity */

@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # ---- constants mirrored from the header
 STAGE_GENERATE, STAGE_ROTATE, STAGE_OBSERVE = 1, 2, 4
@@ -31,7 +31,8 @@ _i32, _f64, _vp, _i64, _u64 = C.c_int32, C.c_double, C.c_void_p, C.c_int64, C.c_
 class SSFunc(C.Structure):
     _fields_ = [("kind", _i32), ("n", _i32), ("x_off", _i32), ("c_off", _i32),
                 ("xmin", _f64), ("xmax", _f64), ("p", _f64 * 4),
-                ("n2", _i32), ("x2_off", _i32), ("c2_off", _i32), ("pad_", _i32)]
+                ("n2", _i32), ("x2_off", _i32), ("c2_off", _i32), ("g_n", _i32),
+                ("g_off", _i32), ("pad_", _i32), ("g_x0", _f64), ("g_inv", _f64)]
 
 
 class SSParams(C.Structure):
@@ -43,9 +44,10 @@ class SSParams(C.Structure):
         ("dist_center", SSFunc), ("dist_spread", SSFunc),
         ("track_sampler", _i32), ("dist_sampler", _i32), ("has_dist", _i32), ("has_iso", _i32),
         ("iso_n", _i32), ("iso_mass_off", _i32), ("iso_mag_off", _i32 * 2),
-        ("iso_slope_off", _i32 * 2), ("imf_n", _i32), ("imf_cdf_off", _i32),
+        ("iso_guide_n", _i32), ("iso_guide_off", _i32), ("imf_n", _i32), ("imf_cdf_off", _i32),
         ("imf_guide_n", _i32), ("imf_guide_off", _i32), ("cdf_guide_off", _i32), ("pad0_", _i32),
         ("imf_mass_lo", _f64), ("imf_mass_hi", _f64), ("imf_mass_step", _f64),
+        ("iso_guide_x0", _f64), ("iso_guide_inv", _f64),
         ("R", _f64 * 9),
         ("nside_pix", _i32), ("nside_ebv", _i32), ("nside_maglim", _i32 * 2),
         ("band_present", _i32 * 2), ("completeness_band", _i32),

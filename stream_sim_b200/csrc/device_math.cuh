@@ -57,20 +57,57 @@ __device__ __forceinline__ int search_le(const double* __restrict__ xp, int lo, 
   return lo;
 }
 
+// Uniform-bucket guide over a sorted table: bucket g = floor((x - x0) * inv) maps to
+// guide[g] = last knot <= the bucket's left edge, so the knot interval of x is found
+// with a short forward scan instead of a binary search (the backward step only
+// absorbs rounding of the bucket index at bucket edges).  The guide is int32 data
+// stored inside the double blob; g_off is in doubles.
+struct Guide {
+  const int32_t* __restrict__ g;
+  int n;            // buckets (0 = no guide: binary search)
+  double x0, inv;
+};
+
+__device__ __forceinline__ Guide guide_of(const SSFunc& f, const double* __restrict__ tab) {
+  Guide G;
+  G.g = reinterpret_cast<const int32_t*>(tab + f.g_off);
+  G.n = f.g_n;
+  G.x0 = f.g_x0;
+  G.inv = f.g_inv;
+  return G;
+}
+
+// last j in [0, n) with xp[j] <= x; requires xp[0] <= x <= xp[n-1]
+__device__ __forceinline__ int locate(const double* __restrict__ xp, int n, const Guide& G, double x) {
+  if (G.n <= 0) return search_le(xp, 0, n, x);
+  int b = (int)((x - G.x0) * G.inv);
+  b = max(0, min(b, G.n - 1));
+  int j = G.g[b];
+  while (j > 0 && xp[j] > x) --j;
+  while (j + 1 < n && xp[j + 1] <= x) ++j;
+  return j;
+}
+
 // np.interp(x, xp, fp, left=fill_lo, right=fill_hi) with host-precomputed slopes
 // (numpy/_core/src/multiarray/compiled_base.c arr_interp): NaN x -> NaN, exact knot
 // hit -> fp[j], otherwise slope*(x - xp[j]) + fp[j] in un-fused double arithmetic.
-__device__ __forceinline__ double lin_eval(const double* __restrict__ xp,
-                                           const double* __restrict__ fp,
-                                           const double* __restrict__ sl, int n, double x,
-                                           double fill_lo, double fill_hi) {
+// lin_at evaluates at an already located interval (tables sharing their abscissae,
+// e.g. the Pal 5 track centre and width, are located once).
+__device__ __forceinline__ double lin_at(const double* __restrict__ xp, const double* __restrict__ fp,
+                                         int n, int j, double x) {
+  const double xj = xp[j], fj = fp[j];
+  if (j == n - 1 || xj == x) return fj;
+  return __dadd_rn(__dmul_rn(fp[n + j], __dsub_rn(x, xj)), fj);
+}
+
+__device__ __forceinline__ double lin_eval(const SSFunc& f, const double* __restrict__ tab,
+                                           double x, double fill_lo, double fill_hi) {
+  const double* __restrict__ xp = tab + f.x_off;
+  const int n = f.n;
   if (x != x) return x;
   if (x < xp[0]) return fill_lo;
   if (x > xp[n - 1]) return fill_hi;
-  const int j = search_le(xp, 0, n, x);
-  const double xj = xp[j], fj = fp[j];
-  if (j == n - 1 || xj == x) return fj;
-  return __dadd_rn(__dmul_rn(sl[j], __dsub_rn(x, xj)), fj);
+  return lin_at(xp, tab + f.c_off, n, locate(xp, n, guide_of(f, tab), x), x);
 }
 
 // scipy CubicSpline(bc_type='natural', extrapolate=False)(x): PPoly in powers of
@@ -102,7 +139,7 @@ __device__ __forceinline__ double fn_eval(const SSFunc& f, const double* __restr
       break;
     }
     case SS_FN_LINEAR:
-      y = lin_eval(tab + f.x_off, tab + f.c_off, tab + f.c_off + f.n, f.n, x, nan_d(), nan_d());
+      y = lin_eval(f, tab, x, nan_d(), nan_d());
       break;
     case SS_FN_SPLINE:
       y = spline_eval(tab + f.x_off, tab + f.c_off, f.n, x);
@@ -236,8 +273,7 @@ __device__ __forceinline__ double photo_error(const SSParams& p, const double* _
     const SSFunc& f = p.photo_error;
     const double loge = (delta <= p.delta_saturation && mag >= sat)
                             ? p.log_err_at_dsat
-                            : lin_eval(tab + f.x_off, tab + f.c_off, tab + f.c_off + f.n, f.n,
-                                       delta, 1.0, 1.0);
+                            : lin_eval(f, tab, delta, 1.0, 1.0);
     stat = exp10(loge);
   }
   const double sys = p.sys_error[band];
@@ -253,7 +289,7 @@ __device__ __forceinline__ double efficiency(const SSParams& p, const SSFunc& f,
   if (mag < sat) return 0.0;
   const double delta = __dsub_rn(mag, maglim);
   if (mag > sat && delta <= p.delta_saturation) return 1.0;
-  return lin_eval(tab + f.x_off, tab + f.c_off, tab + f.c_off + f.n, f.n, delta, 0.0, 0.0);
+  return lin_eval(f, tab, delta, 0.0, 0.0);
 }
 
 }  // namespace ss

@@ -101,8 +101,25 @@ __device__ __forceinline__ void put(void* col, unsigned long long i, double v) {
 __device__ __forceinline__ double track_sample(const SSFunc& fc, const SSFunc& fs, int sampler,
                                                const double* tab, double x, double draw,
                                                unsigned& domain_err) {
-  const double c = ss::fn_eval(fc, tab, x);
-  const double s = ss::fn_eval(fs, tab, x);
+  double c, s;
+  if (fc.kind == SS_FN_LINEAR && fs.kind == SS_FN_LINEAR && fc.x_off == fs.x_off &&
+      fc.n == fs.n) {
+    // centre and width tabulated on the same abscissae (e.g. Pal 5): locate once
+    const double* __restrict__ xp = tab + fc.x_off;
+    const int n = fc.n;
+    if (x >= xp[0] && x <= xp[n - 1]) {
+      const int j = ss::locate(xp, n, ss::guide_of(fc, tab), x);
+      c = ss::lin_at(xp, tab + fc.c_off, n, j, x);
+      s = ss::lin_at(xp, tab + fs.c_off, n, j, x);
+    } else {
+      c = s = ss::nan_d();
+    }
+    if (!(x >= fc.xmin && x <= fc.xmax)) c = ss::nan_d();
+    if (!(x >= fs.xmin && x <= fs.xmax)) s = ss::nan_d();
+  } else {
+    c = ss::fn_eval(fc, tab, x);
+    s = ss::fn_eval(fs, tab, x);
+  }
   if (sampler == SS_SAMPLER_GAUSSIAN) {
     if (!(s >= 0.0)) domain_err++;
     return __dadd_rn(__dmul_rn(draw, s), c);
@@ -126,7 +143,7 @@ __device__ __forceinline__ double invcdf_phi1(const KArgs& a, const int32_t* __r
     const double2* __restrict__ cp = reinterpret_cast<const double2*>(a.t.cdf_pairs);
     int lo = 0, hi = n;
     if (p.cdf_guide_n > 0 && u >= 0.0 && u < 1.0) {
-      const int32_t* guide = itab + p.cdf_guide_off;
+      const int32_t* guide = itab + 2 * p.cdf_guide_off;
       const int g = (int)(u * (double)p.cdf_guide_n);
       lo = guide[g];
       hi = guide[g + 1] + 1;
@@ -158,14 +175,15 @@ __device__ __forceinline__ void iso_sample(const SSParams& p, const double* __re
     m1 = m2 = ss::nan_d();
     return;
   }
-  int lo = 0, hi = n;
+  int j;
   if (p.imf_guide_n > 0 && u >= 0.0 && u < 1.0) {
-    const int32_t* guide = itab + p.imf_guide_off;
-    const int g = (int)(u * (double)p.imf_guide_n);
-    lo = guide[g];
-    hi = min(guide[g + 1] + 1, n);
+    // guide[g] = last cdf entry <= g/G <= u: short forward scan
+    const int32_t* guide = itab + 2 * p.imf_guide_off;
+    j = guide[(int)(u * (double)p.imf_guide_n)];
+    while (j + 1 < n && cdf[j + 1] <= u) ++j;
+  } else {
+    j = ss::search_le(cdf, 0, n, u);
   }
-  const int j = ss::search_le(cdf, lo, hi, u);
   const double mj = (j == n - 1) ? p.imf_mass_hi
                                  : __dadd_rn(__dmul_rn((double)j, p.imf_mass_step), p.imf_mass_lo);
   double mass;
@@ -186,16 +204,14 @@ __device__ __forceinline__ void iso_sample(const SSParams& p, const double* __re
     m1 = m2 = ss::nan_d();
     return;
   }
-  const int k = ss::search_le(mi, 0, ni, mass);
-  const double xk = mi[k];
-  if (k == ni - 1 || xk == mass) {
-    m1 = tab[p.iso_mag_off[0] + k];
-    m2 = tab[p.iso_mag_off[1] + k];
-  } else {
-    const double dx = __dsub_rn(mass, xk);
-    m1 = __dadd_rn(__dmul_rn(tab[p.iso_slope_off[0] + k], dx), tab[p.iso_mag_off[0] + k]);
-    m2 = __dadd_rn(__dmul_rn(tab[p.iso_slope_off[1] + k], dx), tab[p.iso_mag_off[1] + k]);
-  }
+  ss::Guide G;
+  G.g = itab + 2 * p.iso_guide_off;
+  G.n = p.iso_guide_n;
+  G.x0 = p.iso_guide_x0;
+  G.inv = p.iso_guide_inv;
+  const int k = ss::locate(mi, ni, G, mass);
+  m1 = ss::lin_at(mi, tab + p.iso_mag_off[0], ni, k, mass);
+  m2 = ss::lin_at(mi, tab + p.iso_mag_off[1], ni, k, mass);
 }
 
 // ---------------------------------------------------------------- the star kernel
@@ -391,16 +407,25 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
         const double ext = __dmul_rn(p.coeff_extinc[b], ebv);          // surveys.py:228
         const double m_true = __dadd_rn(mag, ext);                     // observed.py:167
         const double err = ss::photo_error(p, tab, b, m_true, maglim); // surveys.py:234-292
-        // sample_measured_magnitudes (observed.py:863-904, :984-1035)
-        const double flux = __dmul_rn(3631.0, exp10(__dmul_rn(-0.4, m_true)));
-        const double sig = __ddiv_rn(__dmul_rn(flux, err), 1.0857362);
-        const double fobs = __dadd_rn(flux, __dmul_rn(sig, zf));
-        const bool good = fobs > 0.0;
+        // sample_measured_magnitudes (observed.py:863-904, :984-1035):
+        //   F = 3631*10^(-0.4 m), F_obs = F + (F*err/1.0857362)*z, m_obs = -2.5 log10(F_obs/3631)
+        // For magnitudes whose flux neither under- nor overflows this is, to rounding,
+        //   F_obs > 0  <=>  t > 0,   m_obs = m - 2.5 log10(t),   t = 1 + (err/1.0857362)*z
+        // which needs one log10 instead of exp10 + log10 + two divisions.
+        bool good;
         double mobs = ss::nan_d();
-        if (good) {
-          mobs = __dmul_rn(-2.5, log10(__ddiv_rn(fobs, 3631.0)));
-          if (p.dust_correction) mobs = __dsub_rn(mobs, ext);          // observed.py:194-208
+        if (fabs(m_true) < 200.0) {
+          const double t = 1.0 + err * (1.0 / 1.0857362) * zf;
+          good = t > 0.0;
+          if (good) mobs = m_true - 2.5 * log10(t);
+        } else {
+          const double flux = __dmul_rn(3631.0, exp10(__dmul_rn(-0.4, m_true)));
+          const double sig = __ddiv_rn(__dmul_rn(flux, err), 1.0857362);
+          const double fobs = __dadd_rn(flux, __dmul_rn(sig, zf));
+          good = fobs > 0.0;
+          if (good) mobs = __dmul_rn(-2.5, log10(__ddiv_rn(fobs, 3631.0)));
         }
+        if (good && p.dust_correction) mobs = __dsub_rn(mobs, ext);    // observed.py:194-208
         valid = valid && good;
         if (!good) { if (b == SS_BAND_G) c_bad_g++; else c_bad_r++; }
         if (p.snr_cut[b]) snr_ok = snr_ok && (err <= p.snr_err_max);   // observed.py:266-281

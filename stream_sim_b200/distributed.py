@@ -1,0 +1,70 @@
+"""Multi-GPU sharding: one process per GPU, stars split by contiguous global
+index range, maps and tables replicated, and a single SUM all-reduce of the
+summary counters + histograms (about 10 KB) as the only collective
+(SURVEY.md section 8e).  Because every draw is keyed by the global star index,
+per-star results are identical for any world size.
+"""
+from __future__ import annotations
+
+import os
+
+
+def shard_range(n_total, rank, world_size):
+    """Contiguous index range [lo, hi) of ``rank``: ceil(n/world) stars per rank,
+    the last ranks possibly short or empty."""
+    n_total, rank, world_size = int(n_total), int(rank), int(world_size)
+    per = -(-n_total // world_size)
+    lo = min(n_total, rank * per)
+    return lo, min(n_total, lo + per)
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed from RANK / WORLD_SIZE / MASTER_* (torchrun).
+    Returns (rank, world_size, local_rank); a no-op single-process world if the
+    variables are absent."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def reduce_counters(counters):
+    """In-place SUM all-reduce of a counters tensor (int64) over all ranks."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(counters, op=dist.ReduceOp.SUM)
+    return counters
+
+
+def max_over_ranks(value, device=None):
+    """Max of a Python float over ranks (used for device-timed durations)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64,
+                     device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def generate_observe_sharded(engine, n_total, seed=0, counters=None, **kw):
+    """Run the fused path for this rank's share of ``n_total`` stars and reduce
+    the counters.  Returns (columns of the local shard, (lo, hi))."""
+    import torch.distributed as dist
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    lo, hi = shard_range(n_total, rank, world)
+    out = engine.generate_observe(hi - lo, seed=seed, offset=lo, counters=counters, **kw)
+    if counters is not None:
+        reduce_counters(counters)
+    return out, (lo, hi)

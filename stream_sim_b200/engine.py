@@ -31,7 +31,7 @@ OBSERVE_COLUMNS = ("mag_g_obs", "mag_r_obs", "magerr_g", "magerr_r", "flag_obser
                    "flag_perfect_galstarsep")
 SNR_MIN = 5.0            # reference observed.py:267
 CDF_GUIDE = 8192
-IMF_GUIDE = 2048
+IMF_GUIDE = 4096
 
 
 def _torch():
@@ -59,18 +59,13 @@ def require_device(device=None):
 
 # ------------------------------------------------------------------ packing
 class BlobPacker:
-    """Accumulates the small tables of one launch configuration.
-
-    Doubles first, int32 guides after; offsets handed out for doubles are in
-    units of doubles from the blob start, int offsets are resolved by
-    :meth:`finalize` (they depend on the total size of the double region).
-    """
+    """Accumulates the small tables of one launch configuration into one buffer of
+    doubles.  int32 search guides are embedded in the same buffer (two per
+    double), so every offset handed out is in units of doubles from the start."""
 
     def __init__(self):
         self._d = []
         self._nd = 0
-        self._i = []
-        self._ni = 0
         self._seen = {}
 
     def add_doubles(self, arr, dedupe=False):
@@ -85,25 +80,43 @@ class BlobPacker:
             self._seen[key] = off
         return off
 
-    def add_ints(self, arr):
+    def add_ints(self, arr, dedupe=False):
+        """int32 data stored inside the double buffer; returns the offset in doubles."""
         arr = np.ascontiguousarray(arr, dtype=np.int32).ravel()
-        off = self._ni
-        self._i.append(arr)
-        self._ni += arr.size
-        return off
+        if arr.size % 2:
+            arr = np.concatenate([arr, np.zeros(1, dtype=np.int32)])
+        return self.add_doubles(arr.view(np.float64), dedupe=dedupe)
+
+    def add_bucket_guide(self, xs):
+        """Uniform-bucket guide over sorted knots ``xs`` (csrc/device_math.cuh
+        ``locate``): returns dict(g_n, g_off, g_x0, g_inv); g_n = 0 for tiny or
+        degenerate tables (binary search on the device)."""
+        xs = np.asarray(xs, dtype=float)
+        n = len(xs)
+        span = xs[-1] - xs[0]
+        if n < 8 or not np.isfinite(span) or span <= 0:
+            return dict(g_n=0, g_off=0, g_x0=0.0, g_inv=0.0)
+        g_n = 1 << int(np.ceil(np.log2(1.5 * n)))
+        inv = g_n / span
+        edges = xs[0] + np.arange(g_n) / inv
+        guide = np.maximum(np.searchsorted(xs, edges, side="right") - 1, 0).astype(np.int32)
+        return dict(g_n=g_n, g_off=self.add_ints(guide, dedupe=True), g_x0=float(xs[0]),
+                    g_inv=float(inv))
 
     def add_linear(self, x, y):
         """interp1d(kind='linear') tables: stable sort by x (scipy's
-        ``argsort(kind='mergesort')``), values, and np.interp's slopes."""
+        ``argsort(kind='mergesort')``), values followed by np.interp's slopes, and a
+        search guide.  Returns a dict of SSFunc fields."""
         x = np.asarray(x, dtype=float)
         y = np.asarray(y, dtype=float)
         order = np.argsort(x, kind="mergesort")
         xs, ys = x[order], y[order]
         with np.errstate(divide="ignore", invalid="ignore"):
             slope = (ys[1:] - ys[:-1]) / (xs[1:] - xs[:-1])
-        x_off = self.add_doubles(xs, dedupe=True)
-        c_off = self.add_doubles(np.concatenate([ys, slope, [0.0]]))
-        return x_off, c_off, len(xs)
+        fields = dict(n=len(xs), x_off=self.add_doubles(xs, dedupe=True),
+                      c_off=self.add_doubles(np.concatenate([ys, slope, [0.0]])))
+        fields.update(self.add_bucket_guide(xs))
+        return fields
 
     def add_spline(self, ppoly):
         """scipy PPoly/CubicSpline: breakpoints and c[4, n-1] (highest power first)."""
@@ -115,17 +128,11 @@ class BlobPacker:
         return x_off, c_off, len(x)
 
     def finalize(self):
-        """-> (uint8 array, int_base): int offsets are ``int_base + local``."""
-        d = np.concatenate(self._d) if self._d else np.zeros(0)
+        """-> uint8 array whose size is a multiple of 16 bytes."""
+        d = np.concatenate(self._d) if self._d else np.zeros(2)
         if d.size % 2:
             d = np.concatenate([d, [0.0]])
-        i = np.concatenate(self._i) if self._i else np.zeros(0, dtype=np.int32)
-        pad = (-i.size) % 4
-        i = np.concatenate([i, np.zeros(pad, dtype=np.int32)])
-        blob = np.concatenate([d.view(np.uint8), i.view(np.uint8)])
-        if blob.size == 0:
-            blob = np.zeros(16, dtype=np.uint8)
-        return blob, d.size * 2
+        return d.view(np.uint8)
 
 
 def search_guide(sorted_vals, guide_n):
@@ -186,19 +193,14 @@ class StarEngine:
         self._keep = []                    # tensors referenced by raw pointers
         packer = BlobPacker()
         p = self.params
-        cdf_guide_local = imf_guide_local = None
         if stream is not None:
-            cdf_guide_local, imf_guide_local = self._describe_stream(stream, packer, int(cdf_steps))
+            self._describe_stream(stream, packer, int(cdf_steps))
         self.set_frame(frame)
         if survey is not None:
             self._describe_survey(survey, packer, bands, nside, dust_correction,
                                   perfect_galstarsep, detection_mag_cut, nest)
         self._describe_hist(hist)
-        blob, int_base = packer.finalize()
-        if cdf_guide_local is not None:
-            p.cdf_guide_off = int_base + cdf_guide_local
-        if imf_guide_local is not None:
-            p.imf_guide_off = int_base + imf_guide_local
+        blob = packer.finalize()
         self.blob = torch.from_numpy(blob).to(self.device)
         self.tables.blob = self.blob.data_ptr()
         self.tables.blob_bytes = self.blob.numel()
@@ -208,7 +210,6 @@ class StarEngine:
         from . import samplers as S
         torch = _torch()
         p = self.params
-        cdf_guide_local = imf_guide_local = None
         dens = stream.density.density if stream.density is not None else None
         if dens is None:
             p.density_kind = _lib.DENSITY_NONE
@@ -223,7 +224,7 @@ class StarEngine:
             xg, pdf = dens.grid(cdf_steps)
             cs, order = S.inverse_cdf_tables(xg, pdf)
             self._set_cdf(xg, cs, order)
-            cdf_guide_local = packer.add_ints(search_guide(cs, CDF_GUIDE))
+            p.cdf_guide_off = packer.add_ints(search_guide(cs, CDF_GUIDE))
             p.cdf_guide_n = CDF_GUIDE
         else:
             raise Exception(f"Unrecognized sampler: {type(dens).__name__}")
@@ -255,10 +256,11 @@ class StarEngine:
                 sg = np.concatenate([(mg[1:] - mg[:-1]) / dm, [0.0]])
                 sr = np.concatenate([(mr[1:] - mr[:-1]) / dm, [0.0]])
             p.iso_mass_off = packer.add_doubles(tab.mass_init)
-            p.iso_mag_off[_lib.BAND_G] = packer.add_doubles(mg)
-            p.iso_mag_off[_lib.BAND_R] = packer.add_doubles(mr)
-            p.iso_slope_off[_lib.BAND_G] = packer.add_doubles(sg)
-            p.iso_slope_off[_lib.BAND_R] = packer.add_doubles(sr)
+            p.iso_mag_off[_lib.BAND_G] = packer.add_doubles(np.concatenate([mg, sg]))
+            p.iso_mag_off[_lib.BAND_R] = packer.add_doubles(np.concatenate([mr, sr]))
+            g = packer.add_bucket_guide(tab.mass_init)
+            p.iso_guide_n, p.iso_guide_off = g["g_n"], g["g_off"]
+            p.iso_guide_x0, p.iso_guide_inv = g["g_x0"], g["g_inv"]
             n = len(tab.cdf)
             lo, hi = float(tab.mass_grid[0]), float(tab.mass_grid[-1])
             step = (hi - lo) / (n - 1)
@@ -268,9 +270,8 @@ class StarEngine:
                 raise AssertionError("IMF mass grid is not reproducible as lo + j*step")
             p.imf_n, p.imf_mass_lo, p.imf_mass_hi, p.imf_mass_step = n, lo, hi, step
             p.imf_cdf_off = packer.add_doubles(tab.cdf)
-            imf_guide_local = packer.add_ints(search_guide(tab.cdf, IMF_GUIDE))
+            p.imf_guide_off = packer.add_ints(search_guide(tab.cdf, IMF_GUIDE))
             p.imf_guide_n = IMF_GUIDE
-        return cdf_guide_local, imf_guide_local
 
     def _set_cdf(self, xg, cs, order):
         """Upload the phi1 inverse-CDF tables (reference samplers.py:69-76)."""
@@ -635,13 +636,12 @@ def sample_inverse_cdf(vals, pdf, size, seed=None, u=None, device=None):
     p.density_kind = _lib.DENSITY_INVCDF
     eng._set_cdf(vals, cs, order)
     packer = BlobPacker()
-    local = packer.add_ints(search_guide(cs, CDF_GUIDE))
+    p.cdf_guide_off = packer.add_ints(search_guide(cs, CDF_GUIDE))
     p.cdf_guide_n = CDF_GUIDE
     p.track_center.kind = p.track_spread.kind = _lib.FN_CONSTANT
     p.track_center.xmin = p.track_spread.xmin = -np.inf
     p.track_center.xmax = p.track_spread.xmax = np.inf
-    blob, int_base = packer.finalize()
-    p.cdf_guide_off = int_base + local
+    blob = packer.finalize()
     eng.blob = torch.from_numpy(blob).to(eng.device)
     eng.tables.blob, eng.tables.blob_bytes = eng.blob.data_ptr(), eng.blob.numel()
     eng.set_frame(None)
@@ -707,7 +707,7 @@ def _unit_engine(device, normal):
         p.track_sampler = _lib.SAMPLER_UNIFORM
         p.track_center.p[0] = 0.5
         p.track_spread.p[0] = 0.5
-    blob, _ = BlobPacker().finalize()
+    blob = BlobPacker().finalize()
     eng.blob = torch.from_numpy(blob).to(device)
     eng.tables.blob, eng.tables.blob_bytes = eng.blob.data_ptr(), eng.blob.numel()
     eng.set_frame(None)

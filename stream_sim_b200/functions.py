@@ -148,8 +148,7 @@ class Interpolation(BoundedFunction):
                                           fill_value=np.nan)(xvals)
 
     def describe(self, packer):
-        x_off, c_off, n = packer.add_linear(self.xvals, self.yvals)
-        return self._descriptor(_lib.FN_LINEAR, n=n, x_off=x_off, c_off=c_off)
+        return self._descriptor(_lib.FN_LINEAR, **packer.add_linear(self.xvals, self.yvals))
 
 
 @_register("file", "fileinterpolation")

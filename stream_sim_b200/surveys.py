@@ -42,9 +42,10 @@ class TabulatedFunction:
         return np.where((x_new < self.x[0]) | (x_new > self.x[-1]), self.fill_value, y)
 
     def describe(self, packer):
-        x_off, c_off, n = packer.add_linear(self.x, self.y)
         f = _lib.SSFunc()
-        f.kind, f.n, f.x_off, f.c_off = _lib.FN_LINEAR, n, x_off, c_off
+        f.kind = _lib.FN_LINEAR
+        for k, v in packer.add_linear(self.x, self.y).items():
+            setattr(f, k, v)
         f.xmin, f.xmax = -np.inf, np.inf
         f.p[0] = self.fill_value
         return f
@@ -173,7 +174,7 @@ class Survey:
             p.err_bright = float(10 ** curve(delta_saturation - 1))
         else:
             p.completeness = TabulatedFunction.coerce(which).describe(packer)
-        blob, _ = packer.finalize()
+        blob = packer.finalize()
         blob_t = torch.from_numpy(blob).to(device)
         t = _lib.SSTables()
         t.blob, t.blob_bytes = blob_t.data_ptr(), blob_t.numel()
