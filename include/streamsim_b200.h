@@ -77,7 +77,8 @@ extern "C" {
 #define SS_DTYPE_F32 1
 
 /* Philox4x32-10 draw blocks: counter = (star_lo, star_hi, block, 0),
- * key = (seed_lo, seed_hi).  Each block yields two 53-bit uniforms (U0,U1):
+ * key = (seed_lo, seed_hi).  Each block yields two 52-bit uniforms (U0,U1)
+ * from the word pairs (w0,w1) and (w2,w3): U = ((w_even >> 12) * 2^32 + w_odd) * 2^-52:
  *   block 0: U0 = u_phi1, U1 = u_mass
  *   block 1: Gaussian samplers use Box-Muller(U0,U1) -> (z_phi2, z_dist);
  *            Uniform samplers use U0 for phi2 and U1 for dist

@@ -64,10 +64,11 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return c0, c1, c2, c3
 
 
-def _u53(a, b):
-    """Two 32-bit words -> double in [0,1) with 53 random bits."""
-    return ((a >> np.uint32(5)).astype(np.float64) * 67108864.0
-            + (b >> np.uint32(6)).astype(np.float64)) * (1.0 / 9007199254740992.0)
+def _u52(a, b):
+    """Two 32-bit words -> double in [0,1) with 52 random bits (the device builds
+    the mantissa of a double in [1,2) from them and subtracts 1)."""
+    return ((a >> np.uint32(12)).astype(np.float64) * 4294967296.0
+            + b.astype(np.float64)) * (1.0 / 4503599627370496.0)
 
 
 def philox_block(seed, index, block):
@@ -82,7 +83,7 @@ def philox_block(seed, index, block):
                       (index >> np.uint64(32)).astype(np.uint32),
                       np.uint32(block), np.uint32(0),
                       seed & 0xFFFFFFFF, seed >> 32)
-    return _u53(w[0], w[1]), _u53(w[2], w[3])
+    return _u52(w[0], w[1]), _u52(w[2], w[3])
 
 
 def box_muller(ua, ub):

@@ -117,7 +117,8 @@ SYMBOLS = {
                                   _P(SSOut), _u64, _u64, _u64, _vp, _i64, _u64]),
 }
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libstreamsim_b200.so")
+LIB_PATH = os.environ.get("STREAMSIM_B200_LIB") or os.path.join(
+    os.path.dirname(os.path.abspath(__file__)), "libstreamsim_b200.so")
 _lib = None
 
 

@@ -18,7 +18,9 @@
 
 #include "device_math.cuh"
 
-#define SS_BLOCK 512
+#ifndef SS_BLOCK
+#define SS_BLOCK 1024
+#endif
 
 namespace {
 

@@ -1,0 +1,312 @@
+"""Host-side logic: C-ABI library loads and exports every declared symbol, table
+packing, configuration schema, function evaluators, error behaviour.  CPU only --
+no compute call is made on the library here.
+"""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from stream_sim_b200 import _lib
+
+
+# ------------------------------------------------------------------ C ABI
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "streamsim_b200.h")).read()
+    declared = set(re.findall(r"^\s*(?:int|int64_t|const char\*)\s+(ss_[a-z0-9_]+)\s*\(", header, re.M))
+    assert declared, "no declarations parsed from the header"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.ss_abi_version() == _lib.ABI_VERSION
+    m = re.search(r"#define SS_ABI_VERSION (\d+)", header)
+    assert int(m.group(1)) == _lib.ABI_VERSION
+
+
+def test_struct_mirrors_match_library():
+    lib = _lib.load()
+    sizes = (ctypes.c_int32 * 7)()
+    assert lib.ss_struct_sizes(sizes) == 0
+    assert [ctypes.sizeof(s) for s in _lib._STRUCTS] == list(sizes)
+    assert lib.ss_struct_sizes(None) == -1
+    assert b"NULL" in lib.ss_last_error()
+
+
+def test_header_constants_match_binding():
+    header = open(os.path.join(ROOT, "include", "streamsim_b200.h")).read()
+    defs = dict(re.findall(r"#define (SS_[A-Z0-9_]+) (-?\d+)u?\b", header))
+    assert int(defs["SS_N_COUNTERS"]) == _lib.N_COUNTERS
+    assert int(defs["SS_HIST_BINS"]) == _lib.HIST_BINS
+    assert int(defs["SS_FN_SPLINE_PRODUCT"]) == _lib.FN_SPLINE_PRODUCT
+    assert int(defs["SS_DENSITY_NONE"]) == _lib.DENSITY_NONE
+    assert int(defs["SS_CNT_INSIDE"]) == _lib.CNT_INSIDE
+    assert int(defs["SS_STAGE_OBSERVE"]) == _lib.STAGE_OBSERVE
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from stream_sim_b200.model import StreamModel
+    from stream_sim_b200.utils import parse_config
+    cfg = parse_config("config/toy1_config.yaml")["background"]
+    with pytest.raises(_lib.StreamSimLibraryError, match="no CPU fallback"):
+        StreamModel(cfg).sample(10)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "stream_sim_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "streamsim_oracle" not in text and "oracle." not in text, f
+
+
+# ------------------------------------------------------------------ functions (host face)
+def test_function_known_answers_from_reference_tests(known_answers):
+    from stream_sim_b200.functions import (CubicSplineInterpolation, FileCubicSplineInterpolation,
+                                           LinearDensityCubicSplineInterpolation,
+                                           FileLinearDensityCubicSplineInterpolation)
+    ka = known_answers
+    x = np.array(ka["x"])
+    nan = lambda v: np.array([np.nan if e is None else e for e in v])
+    sp = CubicSplineInterpolation(np.array(ka["spread_nodes"]), np.array(ka["spread_values"]))
+    np.testing.assert_allclose(sp(x), nan(ka["spread_expected"]))
+    fsp = FileCubicSplineInterpolation("./data/patrick_2022_splines.csv", spline_type="spread",
+                                       stream_name="atlas")
+    np.testing.assert_allclose(fsp(x), nan(ka["spread_expected"]))
+    ld = LinearDensityCubicSplineInterpolation(
+        spread_nodes=np.array(ka["spread_nodes"]), spread_node_values=np.array(ka["spread_values"]),
+        intensity_nodes=np.array(ka["intensity_nodes"]),
+        intensity_node_values=np.array(ka["intensity_values"]))
+    np.testing.assert_allclose(ld(x), nan(ka["linear_density_expected"]), atol=1e-7)
+    fld = FileLinearDensityCubicSplineInterpolation(filename="./data/patrick_2022_splines.csv",
+                                                    stream_name="atlas")
+    np.testing.assert_allclose(fld(x), nan(ka["linear_density_expected"]), atol=1e-7)
+
+
+def test_reference_test_file_runs_unchanged_against_this_package():
+    """The reference's tests/test_functions.py, imported as-is, passes against the
+    drop-in ``stream_sim`` alias (only where /root/reference is mounted)."""
+    ref = "/root/reference/tests/test_functions.py"
+    if not os.path.exists(ref):
+        pytest.skip("reference not mounted on this box")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_test_functions", ref)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    import stream_sim.functions as F
+    assert mod.CubicSplineInterpolation is F.CubicSplineInterpolation
+    for name in dir(mod):
+        if name.startswith("test_"):
+            getattr(mod, name)()
+
+
+def test_functions_match_oracle_and_bounds():
+    import streamsim_oracle as oracle
+    from stream_sim_b200.functions import function_factory
+    x = np.linspace(-12, 20, 501)
+    cases = [dict(type="constant", value=2.5), dict(type="line", slope=0.1, intercept=16.5),
+             dict(type="sinusoid", amplitude=0.75, period=9.0, phase=0.3, offset=0.1,
+                  xmin=-9.0, xmax=9.0),
+             dict(type="fileinterpolation", filename="./data/erkal_2016_pal_5_input.csv",
+                  columns=["phi1", "width"]),
+             dict(type="filecubicsplineinterpolation", filename="./data/patrick_2022_splines.csv",
+                  stream_name="phoenix", spline_type="center")]
+    for cfg in cases:
+        kw = dict(cfg)
+        f = function_factory(kw.pop("type"), **kw)
+        assert np.array_equal(f(x), oracle.OFunc(cfg, ROOT)(x), equal_nan=True), cfg["type"]
+    f = function_factory("line", slope=2.0, intercept=1.0, xmin=0.0, xmax=1.0)
+    assert f(0.5) == 2.0 and np.isnan(f(1.5)) and isinstance(f(0.5), float)
+    with pytest.raises(Exception, match="Unrecognized function: nope"):
+        function_factory("nope")
+    from stream_sim_b200.samplers import sampler_factory
+    with pytest.raises(Exception, match="Unrecognized sampler: nope"):
+        sampler_factory("nope")
+
+
+# ------------------------------------------------------------------ packing
+def test_blob_packer_layout_and_guides():
+    from stream_sim_b200.engine import BlobPacker, search_guide, snr_error_threshold
+    pk = BlobPacker()
+    x = np.array([3.0, 1.0, 2.0, 2.0, 5.0, 4.0, 6.0, 7.0, 9.0, 8.0])
+    y = np.arange(10.0)
+    f1 = pk.add_linear(x, y)
+    f2 = pk.add_linear(x, 2 * y)
+    assert f1["x_off"] == f2["x_off"], "shared abscissae are stored once"
+    blob = pk.finalize()
+    assert blob.dtype == np.uint8 and blob.size % 16 == 0
+    d = blob.view(np.float64)
+    xs = d[f1["x_off"]:f1["x_off"] + 10]
+    assert np.array_equal(xs, np.sort(x))
+    ys = d[f1["c_off"]:f1["c_off"] + 10]
+    assert np.array_equal(ys, y[np.argsort(x, kind="mergesort")])       # stable: 2.0 twice keeps order
+    guide = blob.view(np.int32)[2 * f1["g_off"]:2 * f1["g_off"] + f1["g_n"]]
+    edges = f1["g_x0"] + np.arange(f1["g_n"]) / f1["g_inv"]
+    for g, e in zip(guide, edges):
+        assert xs[g] <= e + 1e-12 and (g == len(xs) - 1 or xs[g + 1] > e - 1e-12 or xs[g + 1] == xs[g])
+    cs = np.sort(np.random.default_rng(0).uniform(size=1000))
+    gd = search_guide(cs, 64)
+    for g in range(65):
+        assert gd[g] == max(np.searchsorted(cs, g / 64, side="right") - 1, 0)
+    e = snr_error_threshold(5.0)
+    assert 1.0 / e >= 5.0 and not (1.0 / np.nextafter(e, 1.0) >= 5.0)
+
+
+def test_inverse_cdf_tables_match_scipy_interp1d():
+    """The (sorted cdf, order) pair reproduces interp1d's stable sort, including the
+    non-monotone CDFs of spline densities that dip below zero (atlas, phoenix)."""
+    import scipy.interpolate
+    from stream_sim_b200.samplers import FileLinearDensityCubicSplineInterpolationSampler as S
+    from stream_sim_b200.samplers import inverse_cdf_tables
+    s = S("./data/patrick_2022_splines.csv", "phoenix")
+    xg, pdf = s.grid()
+    cs, order = inverse_cdf_tables(xg, pdf)
+    assert not np.array_equal(order, np.arange(len(order))), "phoenix CDF is non-monotone"
+    cdf = np.cumsum(pdf)
+    cdf /= cdf[-1]
+    fn = scipy.interpolate.interp1d(cdf, list(range(len(cdf))), bounds_error=False, fill_value=0.0)
+    u = np.random.default_rng(0).uniform(size=5000)
+    mine = np.where((u < cs[0]) | (u > cs[-1]), 0.0, np.interp(u, cs, order.astype(float)))
+    assert np.array_equal(mine, fn(u))
+
+
+# ------------------------------------------------------------------ configuration + survey schema
+def test_configs_parse_and_models_build():
+    from stream_sim_b200.model import (BackgroundModel, SplineStreamModel, StreamModel,
+                                       TrackModel)
+    from stream_sim_b200.utils import parse_config
+    for name in ("toy1", "toy2", "pal5"):
+        cfg = parse_config(f"config/{name}_config.yaml")
+        st = dict(cfg["stream"])
+        st.pop("isochrone", None)
+        m = StreamModel(st)
+        assert isinstance(m.track, TrackModel) and m.velocity is None
+        BackgroundModel(cfg["background"])
+        assert float(cfg["stream"]["nstars"]) > 0
+    cfg = parse_config("config/atlas_spline_config.yaml")
+    m = SplineStreamModel(cfg["stream"])           # upstream's raises AttributeError here
+    assert m.distance_modulus is None and m.density is not None
+    assert parse_config("a: {b: 1}") == {"a": {"b": 1}}
+    with pytest.raises(Exception, match="Unrecognized sampler"):
+        StreamModel(dict(density=dict(type="Bogus"), track=st["track"]))
+    # isochrone needs ugali unless a table is given
+    with pytest.raises(ImportError, match="ugali"):
+        StreamModel(parse_config("config/toy1_config.yaml")["stream"])
+
+
+def test_survey_curves_match_oracle_tables():
+    import streamsim_oracle as oracle
+    from stream_sim_b200 import synthetic as syn
+    from stream_sim_b200.surveys import SurveyFactory, TabulatedFunction
+    for first in (-8.0, -10.4, -12.0):
+        eff = syn.efficiency_csv_columns(first=first)
+        err = syn.photo_error_csv_columns(first=first)
+        c = SurveyFactory.completeness_from_arrays(eff["delta_mag"], eff["detection_eff"], -10.4)
+        ox, oy = oracle.completeness_table(eff["delta_mag"], eff["detection_eff"], -10.4)
+        assert np.array_equal(c.x, ox) and np.array_equal(c.y, oy) and c.fill_value == 0.0
+        e = SurveyFactory.photo_error_from_arrays(err["delta_mag"], err["log_mag_err"], -10.4)
+        ox, oy = oracle.photo_error_table(err["delta_mag"], err["log_mag_err"], -10.4)
+        assert np.array_equal(e.x, ox) and np.array_equal(e.y, oy) and e.fill_value == 1.0
+        d = np.linspace(-15, 5, 999)
+        assert np.array_equal(e(d), oracle._interp1d_linear(ox, oy, d, 1.0))
+    import scipy.interpolate
+    f = scipy.interpolate.interp1d([0.0, 1.0], [1.0, 3.0], bounds_error=False, fill_value=0.0)
+    t = TabulatedFunction.coerce(f)
+    assert np.array_equal(t(np.array([-1.0, 0.5, 2.0])), [0.0, 2.0, 0.0])
+
+
+def test_survey_csv_loaders(tmp_path):
+    import pandas as pd
+    from stream_sim_b200 import synthetic as syn
+    from stream_sim_b200.surveys import SurveyFactory
+    p = tmp_path / "eff.csv"
+    pd.DataFrame(syn.efficiency_csv_columns()).to_csv(p, index=False)
+    both = SurveyFactory.set_completeness(str(p), -10.4)
+    det = SurveyFactory.set_completeness(str(p), -10.4, selection="detected")
+    assert both(-5.0) < det(-5.0) <= 1.0
+    with pytest.raises(ValueError, match="Invalid selection"):
+        SurveyFactory.set_completeness(str(p), selection="nope")
+    q = tmp_path / "err.csv"
+    pd.DataFrame(syn.photo_error_csv_columns()).to_csv(q, index=False)
+    e = SurveyFactory.set_photo_error(str(q), -10.4)
+    assert float(e(10.0)) == 1.0 and float(e(-20.0)) == 1.0
+
+
+def test_survey_factory_loads_npy_survey(tmp_path):
+    """YAML-driven loader + cache on a self-contained synthetic survey directory."""
+    import pandas as pd
+    from stream_sim_b200 import synthetic as syn
+    from stream_sim_b200.surveys import Survey, SurveyFactory
+    for kind, fn in (("maglim_g", "ml_g.npy"), ("maglim_r", "ml_r.npy"), ("ebv", "ebv.npy")):
+        np.save(tmp_path / fn, syn.healpix_map(kind, 8))
+    pd.DataFrame(syn.efficiency_csv_columns()).to_csv(tmp_path / "eff.csv", index=False)
+    pd.DataFrame(syn.photo_error_csv_columns()).to_csv(tmp_path / "err.csv", index=False)
+    cfg = dict(name="toy", release="r1",
+               survey_files=dict(file_path=str(tmp_path), maglim_map_g="ml_g.npy",
+                                 maglim_map_r="ml_r.npy", ebv_map="ebv.npy",
+                                 completeness="eff.csv", completeness_band="r",
+                                 log_photo_error="err.csv"),
+               survey_properties=dict(bands=["g", "r"], coeff_extinc_g=3.66, sys_error=0.005,
+                                      saturation=16.0, delta_saturation=-10.4))
+    SurveyFactory.clear_cache(verbose=False)
+    sv = Survey.load("toy", "r1", config_file=cfg, verbose=False)
+    assert sv.bands == ["g", "r"] and sv.coeff_extinc == {"g": 3.66, "r": 2.285}
+    assert sv.completeness_band == "r" and sv.delta_saturation == -10.4
+    assert len(sv.maglim_maps["g"]) == 768 and np.isnan(sv.maglim_maps["g"]).any()
+    assert sv.efficiency_detection is not None and sv.log_photo_error is not None
+    assert sv.coverage is not None and set(np.unique(sv.coverage)) <= {0.0, 1.0}
+    assert Survey.load("toy", "r1", verbose=False) is sv            # cached
+    assert SurveyFactory.list_cached_surveys() == ["toy_r1"]
+    Survey.load("toy", "r1", verbose=False, uniform_survey=True,
+                uniform_survey_mask_type=["nan"])
+    flat = SurveyFactory._cached_surveys["toy_r1_uniform"]
+    vals = flat.maglim_maps["r"][~np.isnan(flat.maglim_maps["r"])]
+    assert np.all(vals == vals[0])
+    SurveyFactory.clear_cache("toy", verbose=False)
+    assert SurveyFactory.list_cached_surveys() == []
+    with pytest.raises(FileNotFoundError):
+        Survey.load("nosuch", verbose=False)
+    with pytest.raises(ValueError, match="Band 'i' not available"):
+        sv.get_maglim("i")
+
+
+def test_frames_and_ud_grade():
+    import streamsim_oracle as oracle
+    from stream_sim_b200 import healpix as hp
+    from stream_sim_b200.frames import GreatCircleFrame
+    from stream_sim_b200.synthetic import NOTEBOOK_ENDPOINTS
+    fr = GreatCircleFrame.from_endpoints(*NOTEBOOK_ENDPOINTS)
+    R = oracle.frame_from_endpoints(*NOTEBOOK_ENDPOINTS[0], *NOTEBOOK_ENDPOINTS[1])
+    np.testing.assert_allclose(fr.R, R, atol=1e-15)
+    np.testing.assert_allclose(fr.R @ fr.R.T, np.eye(3), atol=1e-14)
+    assert np.allclose(GreatCircleFrame.coerce(fr.R).R, fr.R)
+    # ud_grade: degrading a map that is constant per parent returns the parent value;
+    # unseen children are ignored; all-unseen parents become UNSEEN
+    coarse = np.arange(48, dtype=float)
+    fine = hp.ud_grade(coarse, 4)
+    assert len(fine) == 192 and np.array_equal(hp.ud_grade(fine, 2), coarse)
+    fine2 = fine.copy()
+    nest = hp.ring2nest(4, np.arange(192))
+    fine2[nest < 4] = np.nan                     # all children of NEST parent 0
+    back = hp.ud_grade(fine2, 2)
+    assert (back == hp.UNSEEN).sum() == 1
+    assert hp.npix2nside(12 * 64 ** 2) == 64
+    with pytest.raises(ValueError):
+        hp.npix2nside(100)
+
+
+def test_shard_ranges_cover_exactly():
+    from stream_sim_b200.distributed import shard_range
+    for n in (0, 1, 7, 8, 1000003):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert all(hi >= lo for lo, hi in spans)
