@@ -280,13 +280,13 @@ def run_gpu(args):
     chunk = min(n_e2e, 1 << 22)
     host = eng.allocate_host(n_e2e, COLUMNS, dtype)
     ws = eng.host_workspace(chunk, dtype)
-    h_blob = eng.blob.cpu().pin_memory()
-    h_cdf = eng.cdf_pairs.cpu().pin_memory()
+    dev_tabs = eng.model_tensors()
+    host_tabs = [t.cpu().pin_memory() for t in dev_tabs]
 
     def e2e_step(k):
         # H2D of this step's inputs: the model tables (the path has no per-star input)
-        eng.blob.copy_(h_blob, non_blocking=True)
-        eng.cdf_pairs.copy_(h_cdf, non_blocking=True)
+        for d, h in zip(dev_tabs, host_tabs):
+            d.copy_(h, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         eng.generate_observe_host(n_e2e, host, ws, chunk, seed=args.seed,
                                   offset=(k * world + rank) * n_e2e, dtype=dtype)
@@ -300,7 +300,7 @@ def run_gpu(args):
     barrier()
     e2e_s = ssd.max_over_ranks(time.perf_counter() - t0, device)
     e2e_value = world * n_e2e * e2e_steps / e2e_s
-    h2d = h_blob.numel() + h_cdf.numel() * 8
+    h2d = sum(h.numel() * h.element_size() for h in host_tabs)
     d2h = n_e2e * bps + 8 * int(host["counters"].numel())
 
     if rank != 0:

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SS_ABI_VERSION 4
+#define SS_ABI_VERSION 5
 
 /* error codes */
 #define SS_OK 0
@@ -67,6 +67,8 @@ extern "C" {
 #define SS_DENSITY_INVCDF 1   /* :55-76,158-161 */
 #define SS_DENSITY_GAUSSIAN 2 /* :123-138 */
 #define SS_DENSITY_NONE 3     /* phi1 always comes from SSCatalog.phi1 */
+#define SS_DENSITY_GRID 4     /* INVCDF with a monotone CDF as a direct lookup: exact
+                                 index thresholds + per-grid-point rows (SSTables.grid_*) */
 
 /* band indices used in every [2] array below */
 #define SS_BAND_G 0
@@ -169,7 +171,8 @@ typedef struct SSParams {
   SSFunc completeness;      /* SS_FN_LINEAR, fill 0.0           (surveys.py:1361-1366) */
   SSFunc detection;         /* detection-only table, used when perfect_galstarsep */
   /* ---- histograms: bin = floor((v - lo) * inv_width), dropped if outside */
-  int32_t hist_enable, pad1_;
+  int32_t hist_enable;
+  int32_t grid_lut_n;       /* SS_DENSITY_GRID: buckets of the u -> index table   */
   double hist_lo[SS_N_HIST], hist_inv_width[SS_N_HIST];
 } SSParams;
 
@@ -179,6 +182,11 @@ typedef struct SSTables {
   const double* cdf_pairs;   /* [cdf_n][2] = (sorted cdf_j, slope_j)              */
   const int32_t* cdf_perm;   /* [cdf_n] original index of sorted entry j; NULL if identity */
   const double* grid;        /* [cdf_n] explicit phi1 grid, or NULL = start + j*step */
+  /* SS_DENSITY_GRID: rows[cdf_n][8] = (thr, x, centre, spread, dm_centre, dm_spread,
+   * sin(radians x), cos(radians x)); thr[k] = smallest u with sample index > k.
+   * lut[g] = sample index at u = g/grid_lut_n, g = 0..grid_lut_n. */
+  const double* grid_rows;
+  const int32_t* grid_lut;
 } SSTables;
 
 typedef struct SSMaps {

@@ -9,13 +9,13 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # ---- constants mirrored from the header
 STAGE_GENERATE, STAGE_ROTATE, STAGE_OBSERVE = 1, 2, 4
 FN_NONE, FN_CONSTANT, FN_LINE, FN_SINUSOID, FN_LINEAR, FN_SPLINE, FN_SPLINE_PRODUCT = range(7)
 SAMPLER_GAUSSIAN, SAMPLER_UNIFORM = 0, 1
-DENSITY_UNIFORM, DENSITY_INVCDF, DENSITY_GAUSSIAN, DENSITY_NONE = 0, 1, 2, 3
+DENSITY_UNIFORM, DENSITY_INVCDF, DENSITY_GAUSSIAN, DENSITY_NONE, DENSITY_GRID = 0, 1, 2, 3, 4
 BAND_G, BAND_R = 0, 1
 BAND_INDEX = {"g": BAND_G, "r": BAND_R}
 DTYPE_F64, DTYPE_F32 = 0, 1
@@ -57,13 +57,13 @@ class SSParams(C.Structure):
         ("delta_saturation", _f64), ("snr_err_max", _f64),
         ("log_err_at_dsat", _f64), ("err_bright", _f64),
         ("photo_error", SSFunc), ("completeness", SSFunc), ("detection", SSFunc),
-        ("hist_enable", _i32), ("pad1_", _i32),
+        ("hist_enable", _i32), ("grid_lut_n", _i32),
         ("hist_lo", _f64 * N_HIST), ("hist_inv_width", _f64 * N_HIST)]
 
 
 class SSTables(C.Structure):
     _fields_ = [("blob", _vp), ("blob_bytes", _i64), ("cdf_pairs", _vp), ("cdf_perm", _vp),
-                ("grid", _vp)]
+                ("grid", _vp), ("grid_rows", _vp), ("grid_lut", _vp)]
 
 
 class SSMaps(C.Structure):

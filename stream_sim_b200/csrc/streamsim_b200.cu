@@ -99,11 +99,9 @@ __device__ __forceinline__ void put(void* col, unsigned long long i, double v) {
   if (col) reinterpret_cast<T*>(col)[i] = (T)v;
 }
 
-// TrackModel.sample (reference model.py:513-544): value = draw*scale + loc
-__device__ __forceinline__ double track_sample(const SSFunc& fc, const SSFunc& fs, int sampler,
-                                               const double* tab, double x, double draw,
-                                               unsigned& domain_err) {
-  double c, s;
+// centre and spread of a TrackModel at x (reference model.py:517-518)
+__device__ __forceinline__ void track_eval(const SSFunc& fc, const SSFunc& fs, const double* tab,
+                                           double x, double& c, double& s) {
   if (fc.kind == SS_FN_LINEAR && fs.kind == SS_FN_LINEAR && fc.x_off == fs.x_off &&
       fc.n == fs.n) {
     // centre and width tabulated on the same abscissae (e.g. Pal 5): locate once
@@ -122,6 +120,11 @@ __device__ __forceinline__ double track_sample(const SSFunc& fc, const SSFunc& f
     c = ss::fn_eval(fc, tab, x);
     s = ss::fn_eval(fs, tab, x);
   }
+}
+
+// TrackModel.sample (reference model.py:513-544): value = draw*scale + loc
+__device__ __forceinline__ double track_draw(double c, double s, int sampler, double draw,
+                                             unsigned& domain_err) {
   if (sampler == SS_SAMPLER_GAUSSIAN) {
     if (!(s >= 0.0)) domain_err++;
     return __dadd_rn(__dmul_rn(draw, s), c);
@@ -131,6 +134,49 @@ __device__ __forceinline__ double track_sample(const SSFunc& fc, const SSFunc& f
   const double scale = __dsub_rn(hi, lo);
   if (!(scale >= 0.0)) domain_err++;
   return __dadd_rn(__dmul_rn(draw, scale), lo);
+}
+
+// One row per point of the phi1 grid (SS_DENSITY_GRID): everything the generate and
+// rotate stages need that depends on phi1 only, evaluated once on the host with the
+// reference's own NumPy/SciPy calls.  64 bytes = two L2 sectors per star.
+struct GridRow {
+  double thr;      // smallest u whose sample index exceeds this row's index
+  double x;        // phi1 grid value
+  double c, s;     // track centre, spread at x
+  double dc, ds;   // distance-modulus centre, spread at x
+  double sinx, cosx;  // sin/cos of radians(x)
+};
+
+// inverse_transform_sample (reference samplers.py:55-76) as a direct lookup: the
+// sample index rint(interp(u)) is a non-decreasing step function of u, so it equals
+// the number of host-computed exact thresholds <= u.  A uniform table over u gives
+// the index at the bucket's edges; the few thresholds inside the bucket settle it.
+__device__ __forceinline__ bool grid_sample(const KArgs& a, double u, GridRow& row) {
+  const SSParams& p = a.p;
+  const int n = p.cdf_n;
+  long long idx;
+  const double2* __restrict__ rows = reinterpret_cast<const double2*>(a.t.grid_rows);
+  if (u != u) return false;
+  if (u < 0.0 || u > p.cdf_last) {
+    idx = 0;                                  // interp1d fill_value = 0.0
+  } else if (u >= 1.0) {
+    idx = n - 1;
+  } else {
+    const int g = (int)(u * (double)p.grid_lut_n);
+    int lo = __ldg(&a.t.grid_lut[g]), hi = __ldg(&a.t.grid_lut[g + 1]);
+    // first idx in [lo, hi] with u < thr[idx]
+    while (hi - lo > 2) {
+      const int mid = (lo + hi) >> 1;
+      if (u >= __ldg(&rows[4 * (size_t)mid].x)) lo = mid + 1; else hi = mid;
+    }
+    while (lo < hi && u >= __ldg(&rows[4 * (size_t)lo].x)) ++lo;
+    idx = lo;
+  }
+  const double2 r0 = __ldg(&rows[4 * (size_t)idx]), r1 = __ldg(&rows[4 * (size_t)idx + 1]);
+  const double2 r2 = __ldg(&rows[4 * (size_t)idx + 2]), r3 = __ldg(&rows[4 * (size_t)idx + 3]);
+  row.thr = r0.x; row.x = r0.y; row.c = r1.x; row.s = r1.y;
+  row.dc = r2.x; row.ds = r2.y; row.sinx = r3.x; row.cosx = r3.y;
+  return true;
 }
 
 // inverse_transform_sample (reference samplers.py:55-76) on the host-built tables
@@ -252,6 +298,9 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
     c_tot++;
     double phi1 = 0, phi2 = 0, dist = ss::nan_d(), mag_g = ss::nan_d(), mag_r = ss::nan_d();
     double ra = 0, dec = 0;
+    bool on_grid = false;   // phi1 came from the grid table: row holds f(phi1) values
+    GridRow row;
+    row.c = row.s = row.dc = row.ds = row.sinx = row.cosx = row.x = 0.0;
 
     // ------------------------------------------------ generate (model.py:106-157)
     if (ST & SS_STAGE_GENERATE) {
@@ -267,6 +316,9 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
       const double phi1_given = a.in.phi1 ? a.in.phi1[i] : ss::nan_d();
       if (phi1_given == phi1_given) {
         phi1 = phi1_given;
+      } else if (p.density_kind == SS_DENSITY_GRID) {
+        on_grid = grid_sample(a, u_phi1, row);
+        phi1 = on_grid ? row.x : ss::nan_d();
       } else if (p.density_kind == SS_DENSITY_UNIFORM) {
         phi1 = __dadd_rn(__dmul_rn(u_phi1, __dsub_rn(p.density_hi, p.density_lo)), p.density_lo);
       } else if (p.density_kind == SS_DENSITY_INVCDF) {
@@ -300,14 +352,21 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
         if (a.d.n_dist) n_dist = a.d.n_dist[i];
       }
       const double phi2_given = a.in.phi2 ? a.in.phi2[i] : ss::nan_d();
-      phi2 = (phi2_given == phi2_given)
-                 ? phi2_given
-                 : track_sample(p.track_center, p.track_spread, p.track_sampler, tab, phi1, n_phi2, c_dom);
+      if (phi2_given == phi2_given) {
+        phi2 = phi2_given;
+      } else {
+        double c = row.c, s = row.s;
+        if (!on_grid) track_eval(p.track_center, p.track_spread, tab, phi1, c, s);
+        phi2 = track_draw(c, s, p.track_sampler, n_phi2, c_dom);
+      }
       const double dist_given = a.in.dist ? a.in.dist[i] : ss::nan_d();
       if (dist_given == dist_given) dist = dist_given;
       if (p.has_dist || p.has_iso) {
-        if (!(dist_given == dist_given) && p.has_dist)
-          dist = track_sample(p.dist_center, p.dist_spread, p.dist_sampler, tab, phi1, n_dist, c_dom);
+        if (!(dist_given == dist_given) && p.has_dist) {
+          double c = row.dc, s = row.ds;
+          if (!on_grid) track_eval(p.dist_center, p.dist_spread, tab, phi1, c, s);
+          dist = track_draw(c, s, p.dist_sampler, n_dist, c_dom);
+        }
         if (p.has_iso) {
           double m1, m2;
           iso_sample(p, tab, itab, u_mass, m1, m2, c_dom);
@@ -328,8 +387,8 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
         phi1 = a.in.phi1[i];
         phi2 = a.in.phi2[i];
       }
-      double sl, cl, sb, cb;
-      sincospi(phi1 * (1.0 / 180.0), &sl, &cl);
+      double sl = row.sinx, cl = row.cosx, sb, cb;
+      if (!on_grid) sincospi(phi1 * (1.0 / 180.0), &sl, &cl);
       sincospi(phi2 * (1.0 / 180.0), &sb, &cb);
       const double v0 = cb * cl, v1 = cb * sl, v2 = sb;
       const double wx = p.R[0] * v0 + p.R[3] * v1 + p.R[6] * v2;
@@ -623,6 +682,10 @@ int validate(uint32_t st, const SSParams* p, const SSTables* t, const SSMaps* m,
     if (p->has_dist) {
       if ((rc = check_func(p->dist_center, nd, "distance_modulus.center"))) return rc;
       if ((rc = check_func(p->dist_spread, nd, "distance_modulus.spread"))) return rc;
+    }
+    if (p->density_kind == SS_DENSITY_GRID) {
+      if (!t->grid_rows || !t->grid_lut || p->cdf_n < 2 || p->grid_lut_n < 1)
+        return fail(SS_EINVAL, "grid density needs grid_rows and grid_lut%s");
     }
     if (p->density_kind == SS_DENSITY_INVCDF) {
       if (!t->cdf_pairs || p->cdf_n < 2) return fail(SS_EINVAL, "inverse-CDF density needs cdf_pairs%s");

@@ -32,6 +32,7 @@ OBSERVE_COLUMNS = ("mag_g_obs", "mag_r_obs", "magerr_g", "magerr_r", "flag_obser
 SNR_MIN = 5.0            # reference observed.py:267
 CDF_GUIDE = 8192
 IMF_GUIDE = 4096
+GRID_LUT = 1 << 17
 
 
 def _torch():
@@ -141,6 +142,49 @@ def search_guide(sorted_vals, guide_n):
     return np.maximum(np.searchsorted(sorted_vals, edges, side="right") - 1, 0).astype(np.int32)
 
 
+def invcdf_index(cs, u):
+    """Sample index of ``inverse_transform_sample`` for uniforms ``u`` given the
+    sorted (monotone) CDF ``cs``: rint(interp1d(cs, arange, fill_value=0)(u))
+    (reference samplers.py:71-75)."""
+    u = np.asarray(u, dtype=float)
+    y = np.interp(u, cs, np.arange(len(cs), dtype=float))
+    y = np.where((u < cs[0]) | (u > cs[-1]), 0.0, y)
+    return np.rint(y).astype(np.int64)
+
+
+def invcdf_thresholds(cs):
+    """thr[k] = smallest double u in [0, 1] with invcdf_index(u) >= k+1, found by
+    bisection on the bit patterns of the doubles, so that on the device
+    ``index(u) = #{k : thr[k] <= u}`` reproduces the reference arithmetic exactly.
+    Returns None when the index is not a monotone function of u."""
+    n = len(cs)
+    k = np.arange(n - 1, dtype=np.int64)
+    f0 = int(invcdf_index(cs, np.zeros(1))[0])
+    lo = np.zeros(n - 1, dtype=np.int64)
+    hi = np.full(n - 1, np.array(1.0).view(np.int64), dtype=np.int64)
+    active = k >= f0
+    for _ in range(64):
+        todo = active & (hi - lo > 1)
+        if not todo.any():
+            break
+        mid = lo + (hi - lo) // 2
+        ge = invcdf_index(cs, mid.view(np.float64)) >= k + 1
+        hi = np.where(todo & ge, mid, hi)
+        lo = np.where(todo & ~ge, mid, lo)
+    thr = hi.view(np.float64).copy()
+    thr[~active] = 0.0
+    if np.any(np.diff(thr) < 0):
+        return None
+    # validate against the reference arithmetic, including the thresholds themselves
+    rng = np.random.default_rng(12345)
+    probe = np.concatenate([rng.uniform(size=200000), thr, np.nextafter(thr, -1.0),
+                            [0.0, np.nextafter(1.0, 0.0)]])
+    probe = probe[(probe >= 0.0) & (probe < 1.0)]
+    if not np.array_equal(np.searchsorted(thr, probe, side="right"), invcdf_index(cs, probe)):
+        return None
+    return thr
+
+
 def snr_error_threshold(snr_min=SNR_MIN):
     """Largest magerr e with fl(1/e) >= snr_min: turns the reference's
     ``1.0/magerr >= 5.0`` (observed.py:278-279) into one compare, bit-exactly."""
@@ -181,7 +225,8 @@ class StarEngine:
 
     def __init__(self, stream=None, survey=None, frame=None, device=None, bands=("r", "g"),
                  nside=4096, dust_correction=True, perfect_galstarsep=False,
-                 detection_mag_cut=("g",), nest=False, hist=None, cdf_steps=1e5):
+                 detection_mag_cut=("g",), nest=False, hist=None, cdf_steps=1e5,
+                 grid_table=True):
         torch = _torch()
         self.lib = _lib.load()
         self.device = require_device(device)
@@ -193,6 +238,7 @@ class StarEngine:
         self._keep = []                    # tensors referenced by raw pointers
         packer = BlobPacker()
         p = self.params
+        self._grid_table = bool(grid_table)
         if stream is not None:
             self._describe_stream(stream, packer, int(cdf_steps))
         self.set_frame(frame)
@@ -226,6 +272,8 @@ class StarEngine:
             self._set_cdf(xg, cs, order)
             p.cdf_guide_off = packer.add_ints(search_guide(cs, CDF_GUIDE))
             p.cdf_guide_n = CDF_GUIDE
+            if self._grid_table and p.cdf_identity and not self.tables.grid:
+                self._set_grid_table(stream, xg, cs)
         else:
             raise Exception(f"Unrecognized sampler: {type(dens).__name__}")
 
@@ -298,6 +346,37 @@ class StarEngine:
         if not np.array_equal(ref, xg):      # arbitrary `vals`: ship the grid itself
             self.grid = torch.from_numpy(np.ascontiguousarray(xg, dtype=float)).to(self.device)
             self.tables.grid = self.grid.data_ptr()
+
+    def _set_grid_table(self, stream, xg, cs):
+        """SS_DENSITY_GRID: exact index thresholds + one 64-byte row per grid point
+        holding every phi1-only quantity of the generate/rotate stages, evaluated
+        with the host (reference) functions."""
+        torch = _torch()
+        thr = invcdf_thresholds(cs)
+        if thr is None:
+            return
+        n = len(cs)
+        with np.errstate(invalid="ignore"):
+            c, s = stream.track.center(xg), stream.track.spread(xg)
+            if stream.distance_modulus is not None:
+                dc, ds = stream.distance_modulus.center(xg), stream.distance_modulus.spread(xg)
+            else:
+                dc = ds = np.zeros(n)
+        rad = np.radians(xg)
+        rows = np.stack([np.concatenate([thr, [np.inf]]), xg, c, s, dc, ds, np.sin(rad),
+                         np.cos(rad)], axis=1)
+        lut = np.searchsorted(thr, np.arange(GRID_LUT + 1) / GRID_LUT, side="right")
+        self.grid_rows = torch.from_numpy(np.ascontiguousarray(rows, dtype=np.float64)).to(self.device)
+        self.grid_lut = torch.from_numpy(lut.astype(np.int32)).to(self.device)
+        self.tables.grid_rows = self.grid_rows.data_ptr()
+        self.tables.grid_lut = self.grid_lut.data_ptr()
+        self.params.grid_lut_n = GRID_LUT
+        self.params.density_kind = _lib.DENSITY_GRID
+
+    def model_tensors(self):
+        """Device tensors that make up the model/survey tables (not the maps)."""
+        names = ("blob", "cdf_pairs", "cdf_perm", "grid", "grid_rows", "grid_lut")
+        return [getattr(self, k) for k in names if getattr(self, k, None) is not None]
 
     # ---- rotate
     def set_frame(self, frame):

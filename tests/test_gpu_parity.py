@@ -122,13 +122,15 @@ def _oracle_fused(cfg_name, draws, compl_band="r", **kw):
                                    oracle_survey(compl_band), draws, **kw)
 
 
-@pytest.mark.parametrize("cfg_name", ["toy1", "pal5"])
-def test_fused_free_running_matches_oracle(torch_cuda, cfg_name):
+@pytest.mark.parametrize("cfg_name,grid_table", [("toy1", True), ("pal5", True), ("pal5", False)])
+def test_fused_free_running_matches_oracle(torch_cuda, cfg_name, grid_table):
     """Free-running (Philox on the device) fused generate->rotate->observe equals
     the oracle fed with the same Philox-derived draws: pixel indices and flags
     bit-exact, everything else to 1e-9."""
     n, seed, offset = 1 << 18, 12345, 1000
-    eng, _ = _fused_engine(cfg_name, perfect_galstarsep=True)
+    eng, _ = _fused_engine(cfg_name, perfect_galstarsep=True, grid_table=grid_table)
+    from stream_sim_b200 import _lib
+    assert (eng.params.density_kind == _lib.DENSITY_GRID) == (grid_table and cfg_name == "pal5")
     cnt = eng.new_counters()
     out = eng.generate_observe(n, seed=seed, offset=offset, counters=cnt, pix=True)
     got = {k: v.cpu().numpy() for k, v in out.items()}
