@@ -348,6 +348,21 @@ def random_endpoints(rng):
     return ra, dec
 
 
+def find_frame(rng, phi1, phi2, mask, percentile_threshold=0.99, max_iter=1000):
+    """StreamInjector._find_gc_frame (observed.py:651-679): first random frame whose
+    fraction of stars inside the boolean RING mask reaches the threshold.
+    Returns (R, endpoints, trials, fraction) or None."""
+    nside = npix2nside(len(mask))
+    for trial in range(1, max_iter + 1):
+        e1, e2 = random_endpoints(rng), random_endpoints(rng)
+        R = frame_from_endpoints(*e1, *e2)
+        ra, dec = rotate(phi1, phi2, R)
+        frac = np.count_nonzero(mask[ang2pix_ring(nside, ra, dec)]) / len(ra)
+        if frac >= percentile_threshold:
+            return R, (e1, e2), trial, frac
+    return None
+
+
 def rotate(phi1, phi2, R):
     """(phi1, phi2) deg in the stream frame -> (ra, dec) deg ICRS."""
     l, b = np.radians(phi1), np.radians(phi2)

@@ -256,7 +256,7 @@ class StarEngine:
         from . import samplers as S
         torch = _torch()
         p = self.params
-        dens = stream.density.density if stream.density is not None else None
+        dens = getattr(stream.density, "density", None)   # DensityModel(None) has no sampler
         if dens is None:
             p.density_kind = _lib.DENSITY_NONE
         elif isinstance(dens, S.UniformSampler):

@@ -44,7 +44,7 @@ class _Parts:
     def __init__(self, density=None, track=None, distance_modulus=None, isochrone=None):
         self.density, self.track = density, track
         self.distance_modulus, self.isochrone = distance_modulus, isochrone
-        if self.track is None:
+        if self.track is None or not hasattr(self.track, "center"):
             self.track = TrackModel(dict(center=dict(type="Constant", value=0.0),
                                          spread=dict(type="Constant", value=0.0)))
 
@@ -161,7 +161,7 @@ class StreamModel(ConfigurableModel):
         missing = {c: self._missing_idx(df, c) for c in ("phi1", "phi2", "dist")}
         fill = {c: need[c] and len(missing[c]) > 0 for c in need}
 
-        if fill["phi1"] and self.density is None:
+        if fill["phi1"] and getattr(self.density, "density", None) is None:
             raise ValueError("Density model is required to sample phi1")
         phi1_ok_after = ("phi1" in df.columns and not df["phi1"].isna().any()) or \
                         ("phi1" in targets)
