@@ -65,7 +65,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -303,6 +303,8 @@ def run_gpu(args):
     h2d = sum(h.numel() * h.element_size() for h in host_tabs)
     d2h = n_e2e * bps + 8 * int(host["counters"].numel())
 
+    if world > 1:
+        dist.destroy_process_group()
     if rank != 0:
         return
     peak, peak_src = measured_peak()

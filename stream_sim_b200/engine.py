@@ -602,6 +602,18 @@ class StarEngine:
         st = _lib.STAGE_GENERATE | _lib.STAGE_ROTATE | _lib.STAGE_OBSERVE
         return self.run(st, n, out, None, draws, seed, offset, counters, dtype)
 
+    def run_summary(self, n_total, seed=0, offset=0, chunk=1 << 28, counters=None):
+        """Counters + histograms only: the fused path over ``n_total`` stars with no
+        per-star column kept (BASELINE config 5: 1e9-1e11 stars).  Launches are
+        queued back to back on the current stream; returns the counters tensor."""
+        counters = self.new_counters() if counters is None else counters
+        done = 0
+        while done < n_total:
+            n = min(chunk, n_total - done)
+            self.generate_observe(n, seed=seed, offset=offset + done, counters=counters, out={})
+            done += n
+        return counters
+
     # ---- host-buffer entry (pinned host memory in, pinned host memory out)
     def host_workspace(self, chunk, dtype="f64"):
         torch = _torch()

@@ -469,17 +469,18 @@ class SurveyFactory:
 
     @staticmethod
     def read_map(path, map_min=None, map_max=None):
-        """Dense RING map from ``.npy`` (native), ``.hsp`` (needs healsparse) or
-        FITS (needs healpy); UNSEEN -> NaN."""
-        ext = os.path.splitext(path)[1].lower()
-        if ext == ".npy":
+        """Dense RING map from ``.npy`` or HEALPix FITS (``.fits``, ``.fits.gz``;
+        native reader, ``fitsio.py``) or ``.hsp`` (needs healsparse).  ``.npy`` and
+        ``.hsp`` maps get UNSEEN -> NaN; FITS maps are returned as ``hp.read_map``
+        returns them (reference surveys.py:1019,1117-1118)."""
+        lower = path.lower()
+        if lower.endswith(".npy"):
             m = np.load(path).astype(np.float64)
-        elif ext == ".hsp":
+            return np.where(m == hp.UNSEEN, np.nan, m)
+        if lower.endswith(".hsp"):
             return SurveyFactory.open_map_sparse(path, map_min=map_min, map_max=map_max)
-        else:
-            import healpy
-            m = np.asarray(healpy.read_map(path), dtype=np.float64)
-        return np.where(m == hp.UNSEEN, np.nan, m) if ext == ".npy" else m
+        from .fitsio import read_healpix_map
+        return read_healpix_map(path)
 
     @staticmethod
     def open_map_sparse(file_path, **kwargs):

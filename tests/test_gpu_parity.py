@@ -202,6 +202,26 @@ def test_observe_host_entry(torch_cuda):
     assert torch_cuda.equal(dev["flag_observed"], full["flag_observed"])
 
 
+def test_summary_only_mode_equals_full_run(torch_cuda):
+    """Counters/histograms-only streaming (no per-star output) gives the same
+    summary as a full run, whatever the chunking."""
+    n = (1 << 21) + 12345
+    eng, _ = _fused_engine("pal5", hist=True)
+    full = eng.new_counters()
+    out = eng.generate_observe(n, seed=8, counters=full)
+    chunked = eng.run_summary(n, seed=8, chunk=300000)
+    assert torch_cuda.equal(full, chunked)
+    s = eng.summarize(full)
+    assert s["n_total"] == n and s["n_observed"] == int(out["flag_observed"].sum())
+    for name in ("phi1", "phi2", "dist", "mag_g", "g_minus_r"):
+        assert 0 < s["hist_" + name].sum() <= n
+    assert s["hist_phi1"].sum() == n          # pal5 phi1 lies inside the default range
+    # histogram of phi1 against numpy
+    lo, hi = eng.hist_ranges["phi1"]
+    ref = np.histogram(out["phi1"].cpu().numpy(), bins=256, range=(lo, hi))[0]
+    assert np.abs(s["hist_phi1"] - ref).sum() <= 4     # edge rounding only
+
+
 # ------------------------------------------------------------------ distributions
 def _ks(sample, ref_sorted):
     sample = np.sort(sample)

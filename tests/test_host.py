@@ -277,6 +277,32 @@ def test_survey_factory_loads_npy_survey(tmp_path):
         sv.get_maglim("i")
 
 
+def test_native_fits_healpix_reader(tmp_path):
+    """Survey ingestion without healpy: HEALPix BINTABLE files, RING/NESTED,
+    1 or 1024 pixels per row, float32/float64, gzip."""
+    from stream_sim_b200 import fitsio, healpix as hp
+    from stream_sim_b200 import synthetic as syn
+    from stream_sim_b200.surveys import SurveyFactory
+    m = syn.healpix_map("maglim_r", 16)
+    m = np.where(np.isnan(m), hp.UNSEEN, m)
+    for name, kw in (("a.fits", {}), ("b.fits.gz", dict(dtype=np.float64, per_row=1)),
+                     ("c.fits", dict(nest=True))):
+        path = str(tmp_path / name)
+        fitsio.write_healpix_map(path, hp.reorder_ring_to_nest(m) if kw.get("nest") else m, **kw)
+        r = SurveyFactory.read_map(path)
+        assert r.dtype == np.float64 and len(r) == len(m)
+        if kw.get("dtype") is np.float64:
+            assert np.array_equal(r, m)
+        else:
+            np.testing.assert_allclose(r, m, rtol=1e-6)
+        assert np.array_equal(fitsio.read_healpix_map(path, nest=True),
+                              hp.reorder_ring_to_nest(r))
+    with pytest.raises(ValueError):
+        bad = tmp_path / "bad.fits"
+        bad.write_bytes(b"not a fits file".ljust(2880))
+        fitsio.read_healpix_map(str(bad))
+
+
 def test_frames_and_ud_grade():
     import streamsim_oracle as oracle
     from stream_sim_b200 import healpix as hp
