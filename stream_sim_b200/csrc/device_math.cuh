@@ -48,6 +48,22 @@ __device__ __forceinline__ void box_muller(double ua, double ub, double& z0, dou
   z1 = r * s;
 }
 
+// sin and cos of a small angle (|b| <= 0.26 rad ~ 15 deg: the transverse stream
+// coordinate) by Taylor series to full double precision -- ~20 FMAs instead of a
+// general-range sincos; larger angles take the library path.
+__device__ __forceinline__ void sincos_small(double b, double& s, double& c) {
+  if (fabs(b) <= 0.26) {
+    const double x = b * b;
+    s = b * (1.0 + x * (-1.0 / 6 + x * (1.0 / 120 + x * (-1.0 / 5040 + x * (1.0 / 362880 +
+        x * (-1.0 / 39916800 + x * (1.0 / 6227020800.0 + x * (-1.0 / 1307674368000.0))))))));
+    c = 1.0 + x * (-0.5 + x * (1.0 / 24 + x * (-1.0 / 720 + x * (1.0 / 40320 +
+        x * (-1.0 / 3628800 + x * (1.0 / 479001600 + x * (-1.0 / 87178291200.0 +
+        x * (1.0 / 20922789888000.0))))))));
+  } else {
+    sincos(b, &s, &c);
+  }
+}
+
 // ---------------------------------------------------------------- table search
 // last j in [lo, hi) with xp[j] <= x.  Requires xp[lo] <= x and (hi == n or xp[hi] > x).
 __device__ __forceinline__ int search_le(const double* __restrict__ xp, int lo, int hi, double x) {

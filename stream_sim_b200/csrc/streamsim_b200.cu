@@ -263,7 +263,10 @@ __device__ __forceinline__ void iso_sample(const SSParams& p, const double* __re
 }
 
 // ---------------------------------------------------------------- the star kernel
-template <uint32_t ST, typename OutT>
+// LEAN = the fused free-running production case, fixed at compile time: no injected
+// draws, no catalog inputs, grid-table density, both bands, RING maps.  It removes the
+// generic branches (and their code) from the hot loop; the launcher selects it.
+template <uint32_t ST, typename OutT, bool LEAN>
 __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ KArgs a) {
   extern __shared__ __align__(16) unsigned char smem_blob[];
   __shared__ unsigned long long s_bar;
@@ -271,6 +274,24 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
   __shared__ unsigned int s_hist[SS_N_HIST * SS_HIST_BINS];
 
   const SSParams& p = a.p;
+  // launch-constant switches; compile-time constants in the LEAN instantiation
+  const double* const d_u_phi1 = LEAN ? nullptr : a.d.u_phi1;
+  const double* const d_u_mass = LEAN ? nullptr : a.d.u_mass;
+  const double* const d_n_phi2 = LEAN ? nullptr : a.d.n_phi2;
+  const double* const d_n_dist = LEAN ? nullptr : a.d.n_dist;
+  const double* const d_z_g = LEAN ? nullptr : a.d.z_flux[SS_BAND_G];
+  const double* const d_z_r = LEAN ? nullptr : a.d.z_flux[SS_BAND_R];
+  const double* const d_u_det = LEAN ? nullptr : a.d.u_det;
+  const double* const d_u_det2 = LEAN ? nullptr : a.d.u_det2;
+  const double* const in_phi1 = LEAN ? nullptr : a.in.phi1;
+  const double* const in_phi2 = LEAN ? nullptr : a.in.phi2;
+  const double* const in_dist = LEAN ? nullptr : a.in.dist;
+  const int density_kind = LEAN ? SS_DENSITY_GRID : p.density_kind;
+  const bool has_dist = LEAN ? true : (p.has_dist != 0);
+  const bool has_iso = LEAN ? true : (p.has_iso != 0);
+  const bool band_g = LEAN ? true : (p.band_present[SS_BAND_G] != 0);
+  const bool band_r = LEAN ? true : (p.band_present[SS_BAND_R] != 0);
+  const int nest = LEAN ? 0 : p.nest;
   const bool want_cnt = a.o.counters != nullptr;
   const bool want_hist = want_cnt && p.hist_enable;
 
@@ -297,7 +318,7 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
     const unsigned long long gi = a.offset + i;
     c_tot++;
     double phi1 = 0, phi2 = 0, dist = ss::nan_d(), mag_g = ss::nan_d(), mag_r = ss::nan_d();
-    double ra = 0, dec = 0;
+    double ra = 0, dec = 0, wx = 0, wy = 0, wz = 0, lon = 0;
     bool on_grid = false;   // phi1 came from the grid table: row holds f(phi1) values
     GridRow row;
     row.c = row.s = row.dc = row.ds = row.sinx = row.cosx = row.x = 0.0;
@@ -305,27 +326,27 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
     // ------------------------------------------------ generate (model.py:106-157)
     if (ST & SS_STAGE_GENERATE) {
       double u_phi1, u_mass;
-      if (a.d.u_phi1 && (a.d.u_mass || !p.has_iso)) {
-        u_phi1 = a.d.u_phi1[i];
-        u_mass = p.has_iso ? a.d.u_mass[i] : 0.0;
+      if (d_u_phi1 && (d_u_mass || !has_iso)) {
+        u_phi1 = d_u_phi1[i];
+        u_mass = has_iso ? d_u_mass[i] : 0.0;
       } else {
         ss::philox_pair(gi, SS_DRAW_BLOCK_POS, a.seed, u_phi1, u_mass);
-        if (a.d.u_phi1) u_phi1 = a.d.u_phi1[i];
-        if (a.d.u_mass) u_mass = a.d.u_mass[i];
+        if (d_u_phi1) u_phi1 = d_u_phi1[i];
+        if (d_u_mass) u_mass = d_u_mass[i];
       }
-      const double phi1_given = a.in.phi1 ? a.in.phi1[i] : ss::nan_d();
+      const double phi1_given = in_phi1 ? in_phi1[i] : ss::nan_d();
       if (phi1_given == phi1_given) {
         phi1 = phi1_given;
-      } else if (p.density_kind == SS_DENSITY_GRID) {
+      } else if (density_kind == SS_DENSITY_GRID) {
         on_grid = grid_sample(a, u_phi1, row);
         phi1 = on_grid ? row.x : ss::nan_d();
-      } else if (p.density_kind == SS_DENSITY_UNIFORM) {
+      } else if (density_kind == SS_DENSITY_UNIFORM) {
         phi1 = __dadd_rn(__dmul_rn(u_phi1, __dsub_rn(p.density_hi, p.density_lo)), p.density_lo);
-      } else if (p.density_kind == SS_DENSITY_INVCDF) {
+      } else if (density_kind == SS_DENSITY_INVCDF) {
         phi1 = invcdf_phi1(a, itab, u_phi1);
-      } else if (p.density_kind == SS_DENSITY_GAUSSIAN) {  // u_phi1 slot carries a normal draw
+      } else if (density_kind == SS_DENSITY_GAUSSIAN) {  // u_phi1 slot carries a normal draw
         double z = u_phi1;
-        if (!a.d.u_phi1) {
+        if (!d_u_phi1) {
           double ua, ub, z1;
           ss::philox_pair(gi, SS_DRAW_BLOCK_DENSITY_Z, a.seed, ua, ub);
           ss::box_muller(ua, ub, z, z1);
@@ -336,38 +357,38 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
       }
 
       double n_phi2, n_dist;
-      if (a.d.n_phi2 && (a.d.n_dist || !p.has_dist)) {
-        n_phi2 = a.d.n_phi2[i];
-        n_dist = p.has_dist ? a.d.n_dist[i] : 0.0;
+      if (d_n_phi2 && (d_n_dist || !has_dist)) {
+        n_phi2 = d_n_phi2[i];
+        n_dist = has_dist ? d_n_dist[i] : 0.0;
       } else {
         double ua, ub;
         ss::philox_pair(gi, SS_DRAW_BLOCK_TRACK, a.seed, ua, ub);
         const bool need_z = (p.track_sampler == SS_SAMPLER_GAUSSIAN) ||
-                            (p.has_dist && p.dist_sampler == SS_SAMPLER_GAUSSIAN);
+                            (has_dist && p.dist_sampler == SS_SAMPLER_GAUSSIAN);
         double z0 = 0, z1 = 0;
         if (need_z) ss::box_muller(ua, ub, z0, z1);
         n_phi2 = (p.track_sampler == SS_SAMPLER_GAUSSIAN) ? z0 : ua;
         n_dist = (p.dist_sampler == SS_SAMPLER_GAUSSIAN) ? z1 : ub;
-        if (a.d.n_phi2) n_phi2 = a.d.n_phi2[i];
-        if (a.d.n_dist) n_dist = a.d.n_dist[i];
+        if (d_n_phi2) n_phi2 = d_n_phi2[i];
+        if (d_n_dist) n_dist = d_n_dist[i];
       }
-      const double phi2_given = a.in.phi2 ? a.in.phi2[i] : ss::nan_d();
+      const double phi2_given = in_phi2 ? in_phi2[i] : ss::nan_d();
       if (phi2_given == phi2_given) {
         phi2 = phi2_given;
       } else {
         double c = row.c, s = row.s;
-        if (!on_grid) track_eval(p.track_center, p.track_spread, tab, phi1, c, s);
+        if (!LEAN && !on_grid) track_eval(p.track_center, p.track_spread, tab, phi1, c, s);
         phi2 = track_draw(c, s, p.track_sampler, n_phi2, c_dom);
       }
-      const double dist_given = a.in.dist ? a.in.dist[i] : ss::nan_d();
+      const double dist_given = in_dist ? in_dist[i] : ss::nan_d();
       if (dist_given == dist_given) dist = dist_given;
-      if (p.has_dist || p.has_iso) {
-        if (!(dist_given == dist_given) && p.has_dist) {
+      if (has_dist || has_iso) {
+        if (!(dist_given == dist_given) && has_dist) {
           double c = row.dc, s = row.ds;
-          if (!on_grid) track_eval(p.dist_center, p.dist_spread, tab, phi1, c, s);
+          if (!LEAN && !on_grid) track_eval(p.dist_center, p.dist_spread, tab, phi1, c, s);
           dist = track_draw(c, s, p.dist_sampler, n_dist, c_dom);
         }
-        if (p.has_iso) {
+        if (has_iso) {
           double m1, m2;
           iso_sample(p, tab, itab, u_mass, m1, m2, c_dom);
           mag_g = __dadd_rn(m1, dist);
@@ -384,20 +405,22 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
     // ------------------------------------------------ rotate (observed.py:573)
     if (ST & SS_STAGE_ROTATE) {
       if (!(ST & SS_STAGE_GENERATE)) {
-        phi1 = a.in.phi1[i];
-        phi2 = a.in.phi2[i];
+        phi1 = in_phi1[i];
+        phi2 = in_phi2[i];
       }
       double sl = row.sinx, cl = row.cosx, sb, cb;
-      if (!on_grid) sincospi(phi1 * (1.0 / 180.0), &sl, &cl);
-      sincospi(phi2 * (1.0 / 180.0), &sb, &cb);
+      if (!LEAN && !on_grid) sincospi(phi1 * (1.0 / 180.0), &sl, &cl);
+      ss::sincos_small(phi2 * 0.017453292519943295, sb, cb);
       const double v0 = cb * cl, v1 = cb * sl, v2 = sb;
-      const double wx = p.R[0] * v0 + p.R[3] * v1 + p.R[6] * v2;
-      const double wy = p.R[1] * v0 + p.R[4] * v1 + p.R[7] * v2;
-      const double wz = p.R[2] * v0 + p.R[5] * v1 + p.R[8] * v2;
+      wx = p.R[0] * v0 + p.R[3] * v1 + p.R[6] * v2;
+      wy = p.R[1] * v0 + p.R[4] * v1 + p.R[7] * v2;
+      wz = p.R[2] * v0 + p.R[5] * v1 + p.R[8] * v2;
       const double R2D = 57.29577951308232;
-      ra = atan2(wy, wx) * R2D;
+      lon = atan2(wy, wx);
+      ra = lon * R2D;
       if (ra < 0.0) ra += 360.0;
-      dec = atan2(wz, sqrt(wx * wx + wy * wy)) * R2D;
+      // |w| = 1 to rounding: asin(w_z) is astropy's atan2(w_z, hypot(w_x, w_y)) to 1 ulp
+      dec = (fabs(wz) <= 1.0 ? asin(wz) : atan2(wz, sqrt(wx * wx + wy * wy))) * R2D;
       put<OutT>(a.o.ra, i, ra);
       put<OutT>(a.o.dec, i, dec);
     }
@@ -409,59 +432,73 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
         dec = a.in.dec[i];
       }
       if (!(ST & SS_STAGE_GENERATE)) {
-        mag_g = p.band_present[SS_BAND_G] ? a.in.mag[SS_BAND_G][i] : ss::nan_d();
-        mag_r = p.band_present[SS_BAND_R] ? a.in.mag[SS_BAND_R][i] : ss::nan_d();
+        mag_g = band_g ? a.in.mag[SS_BAND_G][i] : ss::nan_d();
+        mag_r = band_r ? a.in.mag[SS_BAND_R][i] : ss::nan_d();
       }
-      const ss::HpLoc L = ss::hp_locate(ra, dec);
+      ss::HpLoc L;
+      if ((ST & SS_STAGE_ROTATE) && fabs(wz) < 0.9999 && lon == lon) {
+        // fused path: z = cos(colatitude) = w_z and tt = longitude/(pi/2) straight from
+        // the rotated unit vector (the reference goes through degrees and back; equal to
+        // ~1e-16).  Within 0.8 deg of a pole the reference's own chain is used.
+        L.z = wz;
+        const double v = __dmul_rn(lon, 0.6366197723675813430755350534900574);
+        L.tt = (v < 0.0) ? v + 4.0 : v;
+        if (L.tt >= 4.0) L.tt = 0.0;
+        L.sth = 0.0;
+        L.have_sth = false;
+        L.valid = true;
+      } else {
+        L = ss::hp_locate(ra, dec);
+      }
       double ebv = ss::nan_d(), ml_g = ss::nan_d(), ml_r = ss::nan_d();
       if (L.valid) {
-        const long long pe = ss::hp_pix(L, p.nside_ebv, p.nest);
+        const long long pe = ss::hp_pix(L, p.nside_ebv, nest);
         ebv = __ldg(&a.m.ebv[pe]);
         long long pg = -1;
-        if (p.band_present[SS_BAND_G]) {
+        if (band_g) {
           pg = (p.nside_maglim[SS_BAND_G] == p.nside_ebv) ? pe
-                                                          : ss::hp_pix(L, p.nside_maglim[SS_BAND_G], p.nest);
+                                                          : ss::hp_pix(L, p.nside_maglim[SS_BAND_G], nest);
           ml_g = __ldg(&a.m.maglim[SS_BAND_G][pg]);
         }
-        if (p.band_present[SS_BAND_R]) {
+        if (band_r) {
           const long long pr =
               (p.nside_maglim[SS_BAND_R] == p.nside_ebv) ? pe
               : (pg >= 0 && p.nside_maglim[SS_BAND_R] == p.nside_maglim[SS_BAND_G])
                   ? pg
-                  : ss::hp_pix(L, p.nside_maglim[SS_BAND_R], p.nest);
+                  : ss::hp_pix(L, p.nside_maglim[SS_BAND_R], nest);
           ml_r = __ldg(&a.m.maglim[SS_BAND_R][pr]);
         }
-        if (a.o.pix) a.o.pix[i] = ss::hp_pix(L, p.nside_pix, p.nest);
+        if (a.o.pix) a.o.pix[i] = ss::hp_pix(L, p.nside_pix, nest);
       } else {
         c_coord++;
         if (a.o.pix) a.o.pix[i] = -1;
       }
 
       double z_g, z_r;
-      if (a.d.z_flux[SS_BAND_G] && a.d.z_flux[SS_BAND_R]) {
-        z_g = a.d.z_flux[SS_BAND_G][i];
-        z_r = a.d.z_flux[SS_BAND_R][i];
+      if (d_z_g && d_z_r) {
+        z_g = d_z_g[i];
+        z_r = d_z_r[i];
       } else {
         double ua, ub;
         ss::philox_pair(gi, SS_DRAW_BLOCK_FLUX, a.seed, ua, ub);
         ss::box_muller(ua, ub, z_r, z_g);
-        if (a.d.z_flux[SS_BAND_G]) z_g = a.d.z_flux[SS_BAND_G][i];
-        if (a.d.z_flux[SS_BAND_R]) z_r = a.d.z_flux[SS_BAND_R][i];
+        if (d_z_g) z_g = d_z_g[i];
+        if (d_z_r) z_r = d_z_r[i];
       }
       double u_det, u_det2;
-      if (a.d.u_det && (a.d.u_det2 || !p.perfect_galstarsep)) {
-        u_det = a.d.u_det[i];
-        u_det2 = p.perfect_galstarsep ? a.d.u_det2[i] : 0.0;
+      if (d_u_det && (d_u_det2 || !p.perfect_galstarsep)) {
+        u_det = d_u_det[i];
+        u_det2 = p.perfect_galstarsep ? d_u_det2[i] : 0.0;
       } else {
         ss::philox_pair(gi, SS_DRAW_BLOCK_DETECT, a.seed, u_det, u_det2);
-        if (a.d.u_det) u_det = a.d.u_det[i];
-        if (a.d.u_det2) u_det2 = a.d.u_det2[i];
+        if (d_u_det) u_det = d_u_det[i];
+        if (d_u_det2) u_det2 = d_u_det2[i];
       }
 
       bool valid = true, flag_c = false, flag_d = false, snr_ok = true, snr_r_ok = true;
 #pragma unroll
       for (int b = 0; b < 2; ++b) {
-        if (!p.band_present[b]) continue;
+        if (!(b == SS_BAND_G ? band_g : band_r)) continue;
         const double mag = b == SS_BAND_G ? mag_g : mag_r;
         const double maglim = b == SS_BAND_G ? ml_g : ml_r;
         const double zf = b == SS_BAND_G ? z_g : z_r;
@@ -627,10 +664,10 @@ int plan_launch(const DevInfo& d, int64_t blob_bytes, uint64_t n, int& smem, int
   return SS_OK;
 }
 
-template <uint32_t ST, typename OutT>
+template <uint32_t ST, typename OutT, bool LEAN = false>
 int launch_t(const KArgs& a, int smem, int grid, cudaStream_t stream) {
   static thread_local int configured_smem = -1;
-  auto kern = k_stars<ST, OutT>;
+  auto kern = k_stars<ST, OutT, LEAN>;
   if (smem > configured_smem) {
     SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured_smem = smem;
@@ -648,7 +685,16 @@ int launch_stage(uint32_t st, const KArgs& a, int smem, int grid, cudaStream_t s
     case 3: return launch_t<3, OutT>(a, smem, grid, s);
     case 4: return launch_t<4, OutT>(a, smem, grid, s);
     case 6: return launch_t<6, OutT>(a, smem, grid, s);
-    case 7: return launch_t<7, OutT>(a, smem, grid, s);
+    case 7: {
+      const SSDraws& d = a.d;
+      const bool lean = a.p.density_kind == SS_DENSITY_GRID && !a.p.nest && a.p.has_dist &&
+                        a.p.has_iso && a.p.band_present[0] && a.p.band_present[1] &&
+                        !d.u_phi1 && !d.u_mass && !d.n_phi2 && !d.n_dist && !d.z_flux[0] &&
+                        !d.z_flux[1] && !d.u_det && !d.u_det2 && !a.in.phi1 && !a.in.phi2 &&
+                        !a.in.dist;
+      return lean ? launch_t<7, OutT, true>(a, smem, grid, s)
+                  : launch_t<7, OutT, false>(a, smem, grid, s);
+    }
   }
   return fail(SS_EINVAL, "unsupported stage mask%s");
 }
