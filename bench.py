@@ -207,17 +207,17 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------ GPU arm
-def build_engine(device, nside):
+def build_engine(device, nside, survey=None, math="f64"):
     from helpers import stream_config
     from stream_sim_b200.engine import StarEngine
     from stream_sim_b200.frames import GreatCircleFrame
     from stream_sim_b200.model import StreamModel
     from stream_sim_b200.surveys import Survey
     from stream_sim_b200.synthetic import NOTEBOOK_ENDPOINTS
-    survey = Survey.synthetic(nside, nside, device=device)
+    survey = Survey.synthetic(nside, nside, device=device) if survey is None else survey
     eng = StarEngine(stream=StreamModel(stream_config("pal5")), survey=survey,
                      frame=GreatCircleFrame.from_endpoints(*NOTEBOOK_ENDPOINTS), device=device,
-                     nside=nside, hist=True)
+                     nside=nside, hist=True, math=math)
     return eng, survey
 
 
@@ -272,6 +272,27 @@ def run_gpu(args):
     clocks = sampler.stop() if sampler else None
     value = world * n * args.steps / (total_ms * 1e-3)
     summary = eng.summarize(counters)
+
+    # ---- supplementary: the mixed-precision kernel on the same workload (not the headline)
+    mixed = None
+    if not args.no_mixed:
+        eng_m, _ = build_engine(device, NSIDE, survey=survey, math="mixed")
+        cm = eng_m.new_counters()
+        for k in range(3):
+            eng_m.generate_observe(n, seed=args.seed, offset=k * n, counters=cm, dtype=dtype, out=out)
+        barrier()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record()
+        for k in range(args.steps):
+            eng_m.generate_observe(n, seed=args.seed, offset=((3 + k) * world + rank) * n,
+                                   counters=cm, dtype=dtype, out=out)
+        m1.record()
+        barrier()
+        mixed_ms = ssd.max_over_ranks(m0.elapsed_time(m1), device) / args.steps
+        mixed = {"value": world * n / (mixed_ms * 1e-3), "unit": "stars/s", "ms_per_step": mixed_ms,
+                 "math": "fp32 Box-Muller/10^x/sqrt/log with fp64 fallback near thresholds; "
+                         "pix and flags identical to f64, mags ~1e-6 relative"}
+        del eng_m
 
     # ---- end to end through the C ABI with HOST buffers (pinned), D2H inside
     n_e2e = min(n, args.e2e_stars)
@@ -333,6 +354,9 @@ def run_gpu(args):
         "gpu_launches": args.steps,
         "clocks": clocks,
     }
+    if mixed is not None:
+        mixed["roofline_frac"] = (mixed["value"] / world) * bps / 1e9 / peak
+        line["mixed_precision"] = mixed
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         maps = {k: v.cpu().numpy() for k, v in (("ebv", survey.ebv_map), ("g", survey.maglim_maps["g"]),
@@ -357,6 +381,7 @@ def main():
     ap.add_argument("--seed", type=int, default=12345)
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-mixed", action="store_true", help="skip the mixed-precision leg")
     ap.add_argument("--no-e2e", action="store_true",
                     help="profiling runs: shrink the end-to-end leg to a token size")
     args = ap.parse_args()

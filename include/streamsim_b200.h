@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SS_ABI_VERSION 5
+#define SS_ABI_VERSION 6
 
 /* error codes */
 #define SS_OK 0
@@ -73,6 +73,11 @@ extern "C" {
 /* band indices used in every [2] array below */
 #define SS_BAND_G 0
 #define SS_BAND_R 1
+
+/* arithmetic of the transcendental-heavy steps (SSParams.math_mode) */
+#define SS_MATH_F64 0   /* everything in double: parity grade                          */
+#define SS_MATH_MIXED 1 /* fp32 Box-Muller / 10^x / sqrt / log with double fallback near
+                           decision thresholds: identical pix and flags, mags ~1e-6 rel. */
 
 /* output element type of the floating-point columns */
 #define SS_DTYPE_F64 0
@@ -174,6 +179,8 @@ typedef struct SSParams {
   int32_t hist_enable;
   int32_t grid_lut_n;       /* SS_DENSITY_GRID: buckets of the u -> index table   */
   double hist_lo[SS_N_HIST], hist_inv_width[SS_N_HIST];
+  int32_t math_mode;        /* SS_MATH_*                                          */
+  int32_t pad2_;
 } SSParams;
 
 typedef struct SSTables {

@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # ---- constants mirrored from the header
 STAGE_GENERATE, STAGE_ROTATE, STAGE_OBSERVE = 1, 2, 4
@@ -19,6 +19,7 @@ DENSITY_UNIFORM, DENSITY_INVCDF, DENSITY_GAUSSIAN, DENSITY_NONE, DENSITY_GRID = 
 BAND_G, BAND_R = 0, 1
 BAND_INDEX = {"g": BAND_G, "r": BAND_R}
 DTYPE_F64, DTYPE_F32 = 0, 1
+MATH_F64, MATH_MIXED = 0, 1
 (CNT_TOTAL, CNT_OBSERVED, CNT_PERFECT, CNT_BADMAG_G, CNT_BADMAG_R, CNT_UNSEEN, CNT_DOMAIN,
  CNT_BADCOORD, CNT_INSIDE) = range(9)
 N_COUNTERS, HIST_BINS, N_HIST = 16, 256, 5
@@ -58,7 +59,8 @@ class SSParams(C.Structure):
         ("log_err_at_dsat", _f64), ("err_bright", _f64),
         ("photo_error", SSFunc), ("completeness", SSFunc), ("detection", SSFunc),
         ("hist_enable", _i32), ("grid_lut_n", _i32),
-        ("hist_lo", _f64 * N_HIST), ("hist_inv_width", _f64 * N_HIST)]
+        ("hist_lo", _f64 * N_HIST), ("hist_inv_width", _f64 * N_HIST),
+        ("math_mode", _i32), ("pad2_", _i32)]
 
 
 class SSTables(C.Structure):

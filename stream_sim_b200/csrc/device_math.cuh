@@ -48,6 +48,21 @@ __device__ __forceinline__ void box_muller(double ua, double ub, double& z0, dou
   z1 = r * s;
 }
 
+// Box-Muller in fp32 (mixed-precision mode): the same two uniforms, single-precision
+// log / sqrt / sincos.  The radius uses a short series for small ua, where
+// log(1-ua) computed through log2 would lose relative accuracy.
+__device__ __forceinline__ void box_muller_f32(double ua, double ub, double& z0, double& z1) {
+  const float uf = (float)ua;
+  const float l_series = -uf * (1.0f + uf * (0.5f + uf * (0.33333334f + uf * 0.25f)));
+  const float l_log = __logf((float)(1.0 - ua));
+  const float l = (uf < 0.03f) ? l_series : l_log;
+  const float r = sqrtf(-2.0f * l);
+  float s, c;
+  sincospif(2.0f * (float)ub, &s, &c);
+  z0 = (double)(r * c);
+  z1 = (double)(r * s);
+}
+
 // sin and cos of a small angle (|b| <= 0.26 rad ~ 15 deg: the transverse stream
 // coordinate) by Taylor series to full double precision -- ~20 FMAs instead of a
 // general-range sincos; larger angles take the library path.
@@ -278,23 +293,32 @@ __device__ __forceinline__ long long hp_pix(const HpLoc& L, long long nside, int
 }
 
 // ---------------------------------------------------------------- survey getters
-// Survey.get_photo_error (reference surveys.py:270-290)
-__device__ __forceinline__ double photo_error(const SSParams& p, const double* __restrict__ tab,
-                                              int band, double mag, double maglim) {
+// log10 of the statistical photometric error, Survey.get_photo_error (reference
+// surveys.py:270-286); `bright` is set for saturated stars, whose error is the
+// host-evaluated constant 10**f(dsat-1).
+__device__ __forceinline__ double photo_error_log(const SSParams& p, const double* __restrict__ tab,
+                                                  int band, double mag, double maglim, bool& bright) {
   const double delta = __dsub_rn(mag, maglim);
   const double sat = p.saturation[band];
-  double stat;
-  if (mag < sat) {
-    stat = p.err_bright;
-  } else {
-    const SSFunc& f = p.photo_error;
-    const double loge = (delta <= p.delta_saturation && mag >= sat)
-                            ? p.log_err_at_dsat
-                            : lin_eval(f, tab, delta, 1.0, 1.0);
-    stat = exp10(loge);
-  }
+  bright = mag < sat;
+  if (bright) return 0.0;
+  return (delta <= p.delta_saturation && mag >= sat) ? p.log_err_at_dsat
+                                                     : lin_eval(p.photo_error, tab, delta, 1.0, 1.0);
+}
+
+// statistical (+) systematic error in quadrature (reference surveys.py:288-290)
+__device__ __forceinline__ double photo_error_total(const SSParams& p, int band, double loge,
+                                                    bool bright) {
+  const double stat = bright ? p.err_bright : exp10(loge);
   const double sys = p.sys_error[band];
   return sqrt(__dadd_rn(__dmul_rn(stat, stat), __dmul_rn(sys, sys)));
+}
+
+__device__ __forceinline__ double photo_error(const SSParams& p, const double* __restrict__ tab,
+                                              int band, double mag, double maglim) {
+  bool bright;
+  const double loge = photo_error_log(p, tab, band, mag, maglim, bright);
+  return photo_error_total(p, band, loge, bright);
 }
 
 // Survey.get_efficiency (reference surveys.py:473-493)

@@ -266,7 +266,13 @@ __device__ __forceinline__ void iso_sample(const SSParams& p, const double* __re
 // LEAN = the fused free-running production case, fixed at compile time: no injected
 // draws, no catalog inputs, grid-table density, both bands, RING maps.  It removes the
 // generic branches (and their code) from the hot loop; the launcher selects it.
-template <uint32_t ST, typename OutT, bool LEAN>
+// MATH = SS_MATH_F64: every operation in double (parity grade, 1e-9 of the oracle).
+// MATH = SS_MATH_MIXED: Box-Muller, 10^x, the quadrature sum and the flux-noise log run
+// in fp32 on the MUFU units; any star whose photometric error or noisy flux lands within
+// a guard band of a decision threshold (SNR cut, flux > 0) is recomputed in double, so
+// pixel indices and flags stay bit-identical to the fp64 path while magnitudes agree to
+// ~1e-6 relative (the north star asks 1e-5).
+template <uint32_t ST, typename OutT, bool LEAN, int MATH>
 __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ KArgs a) {
   extern __shared__ __align__(16) unsigned char smem_blob[];
   __shared__ unsigned long long s_bar;
@@ -349,7 +355,8 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
         if (!d_u_phi1) {
           double ua, ub, z1;
           ss::philox_pair(gi, SS_DRAW_BLOCK_DENSITY_Z, a.seed, ua, ub);
-          ss::box_muller(ua, ub, z, z1);
+          if (MATH == SS_MATH_MIXED) ss::box_muller_f32(ua, ub, z, z1);
+          else ss::box_muller(ua, ub, z, z1);
         }
         phi1 = __dadd_rn(__dmul_rn(z, p.density_hi), p.density_lo);
       } else {
@@ -366,7 +373,10 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
         const bool need_z = (p.track_sampler == SS_SAMPLER_GAUSSIAN) ||
                             (has_dist && p.dist_sampler == SS_SAMPLER_GAUSSIAN);
         double z0 = 0, z1 = 0;
-        if (need_z) ss::box_muller(ua, ub, z0, z1);
+        if (need_z) {
+          if (MATH == SS_MATH_MIXED) ss::box_muller_f32(ua, ub, z0, z1);
+          else ss::box_muller(ua, ub, z0, z1);
+        }
         n_phi2 = (p.track_sampler == SS_SAMPLER_GAUSSIAN) ? z0 : ua;
         n_dist = (p.dist_sampler == SS_SAMPLER_GAUSSIAN) ? z1 : ub;
         if (d_n_phi2) n_phi2 = d_n_phi2[i];
@@ -481,7 +491,8 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
       } else {
         double ua, ub;
         ss::philox_pair(gi, SS_DRAW_BLOCK_FLUX, a.seed, ua, ub);
-        ss::box_muller(ua, ub, z_r, z_g);
+        if (MATH == SS_MATH_MIXED) ss::box_muller_f32(ua, ub, z_r, z_g);
+        else ss::box_muller(ua, ub, z_r, z_g);
         if (d_z_g) z_g = d_z_g[i];
         if (d_z_r) z_r = d_z_r[i];
       }
@@ -504,24 +515,50 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
         const double zf = b == SS_BAND_G ? z_g : z_r;
         const double ext = __dmul_rn(p.coeff_extinc[b], ebv);          // surveys.py:228
         const double m_true = __dadd_rn(mag, ext);                     // observed.py:167
-        const double err = ss::photo_error(p, tab, b, m_true, maglim); // surveys.py:234-292
+        bool bright;
+        const double loge = ss::photo_error_log(p, tab, b, m_true, maglim, bright);  // surveys.py:234-286
         // sample_measured_magnitudes (observed.py:863-904, :984-1035):
         //   F = 3631*10^(-0.4 m), F_obs = F + (F*err/1.0857362)*z, m_obs = -2.5 log10(F_obs/3631)
         // For magnitudes whose flux neither under- nor overflows this is, to rounding,
         //   F_obs > 0  <=>  t > 0,   m_obs = m - 2.5 log10(t),   t = 1 + (err/1.0857362)*z
         // which needs one log10 instead of exp10 + log10 + two divisions.
+        double err;
         bool good;
         double mobs = ss::nan_d();
-        if (fabs(m_true) < 200.0) {
-          const double t = 1.0 + err * (1.0 / 1.0857362) * zf;
-          good = t > 0.0;
-          if (good) mobs = m_true - 2.5 * log10(t);
-        } else {
-          const double flux = __dmul_rn(3631.0, exp10(__dmul_rn(-0.4, m_true)));
-          const double sig = __ddiv_rn(__dmul_rn(flux, err), 1.0857362);
-          const double fobs = __dadd_rn(flux, __dmul_rn(sig, zf));
-          good = fobs > 0.0;
-          if (good) mobs = __dmul_rn(-2.5, log10(__ddiv_rn(fobs, 3631.0)));
+        bool done = false;
+        if (MATH == SS_MATH_MIXED) {
+          // fp32 fast path; falls through to the double path near a decision boundary
+          const float sys_f = (float)p.sys_error[b];
+          const float stat_f = bright ? (float)p.err_bright : exp2f((float)loge * 3.3219281f);
+          const float err_f = sqrtf(stat_f * stat_f + sys_f * sys_f);
+          const float thr_f = (float)p.snr_err_max;
+          const float x_f = err_f * (float)(1.0 / 1.0857362) * (float)zf;
+          const float t_f = 1.0f + x_f;
+          // err_f is good to ~1e-6 relative, so t_f carries ~1.5e-6 (1 + |x|) absolute error;
+          // the log amplifies it by 1/t: keep it below ~2.5e-4 mag (1e-5 of a magnitude ~25)
+          const bool safe = fabsf(err_f - thr_f) > 2e-5f * thr_f &&
+                            fabsf(t_f) > 0.012f * (1.0f + fabsf(x_f)) &&
+                            fabs(m_true) < 200.0;          // NaN anywhere -> not safe
+          if (safe) {
+            err = (double)err_f;
+            good = t_f > 0.0f;
+            if (good) mobs = m_true - (double)(0.75257499f * __log2f(t_f));   // 2.5 log10 t
+            done = true;
+          }
+        }
+        if (!done) {
+          err = ss::photo_error_total(p, b, loge, bright);                 // surveys.py:288-290
+          if (fabs(m_true) < 200.0) {
+            const double t = 1.0 + err * (1.0 / 1.0857362) * zf;
+            good = t > 0.0;
+            if (good) mobs = m_true - 2.5 * log10(t);
+          } else {
+            const double flux = __dmul_rn(3631.0, exp10(__dmul_rn(-0.4, m_true)));
+            const double sig = __ddiv_rn(__dmul_rn(flux, err), 1.0857362);
+            const double fobs = __dadd_rn(flux, __dmul_rn(sig, zf));
+            good = fobs > 0.0;
+            if (good) mobs = __dmul_rn(-2.5, log10(__ddiv_rn(fobs, 3631.0)));
+          }
         }
         if (good && p.dust_correction) mobs = __dsub_rn(mobs, ext);    // observed.py:194-208
         valid = valid && good;
@@ -664,10 +701,10 @@ int plan_launch(const DevInfo& d, int64_t blob_bytes, uint64_t n, int& smem, int
   return SS_OK;
 }
 
-template <uint32_t ST, typename OutT, bool LEAN = false>
+template <uint32_t ST, typename OutT, bool LEAN = false, int MATH = SS_MATH_F64>
 int launch_t(const KArgs& a, int smem, int grid, cudaStream_t stream) {
   static thread_local int configured_smem = -1;
-  auto kern = k_stars<ST, OutT, LEAN>;
+  auto kern = k_stars<ST, OutT, LEAN, MATH>;
   if (smem > configured_smem) {
     SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured_smem = smem;
@@ -683,7 +720,9 @@ int launch_stage(uint32_t st, const KArgs& a, int smem, int grid, cudaStream_t s
     case 1: return launch_t<1, OutT>(a, smem, grid, s);
     case 2: return launch_t<2, OutT>(a, smem, grid, s);
     case 3: return launch_t<3, OutT>(a, smem, grid, s);
-    case 4: return launch_t<4, OutT>(a, smem, grid, s);
+    case 4:
+      return a.p.math_mode == SS_MATH_MIXED ? launch_t<4, OutT, false, SS_MATH_MIXED>(a, smem, grid, s)
+                                            : launch_t<4, OutT>(a, smem, grid, s);
     case 6: return launch_t<6, OutT>(a, smem, grid, s);
     case 7: {
       const SSDraws& d = a.d;
@@ -692,6 +731,9 @@ int launch_stage(uint32_t st, const KArgs& a, int smem, int grid, cudaStream_t s
                         !d.u_phi1 && !d.u_mass && !d.n_phi2 && !d.n_dist && !d.z_flux[0] &&
                         !d.z_flux[1] && !d.u_det && !d.u_det2 && !a.in.phi1 && !a.in.phi2 &&
                         !a.in.dist;
+      if (a.p.math_mode == SS_MATH_MIXED)
+        return lean ? launch_t<7, OutT, true, SS_MATH_MIXED>(a, smem, grid, s)
+                    : launch_t<7, OutT, false, SS_MATH_MIXED>(a, smem, grid, s);
       return lean ? launch_t<7, OutT, true>(a, smem, grid, s)
                   : launch_t<7, OutT, false>(a, smem, grid, s);
     }
@@ -716,6 +758,10 @@ int validate(uint32_t st, const SSParams* p, const SSTables* t, const SSMaps* m,
   if (!p || !out) return fail(SS_EINVAL, "params and out must not be NULL%s");
   if (out->dtype != SS_DTYPE_F64 && out->dtype != SS_DTYPE_F32)
     return fail(SS_EINVAL, "SSOut.dtype must be SS_DTYPE_F64 or SS_DTYPE_F32%s");
+  if (p->math_mode != SS_MATH_F64 && p->math_mode != SS_MATH_MIXED)
+    return fail(SS_EINVAL, "SSParams.math_mode must be SS_MATH_F64 or SS_MATH_MIXED%s");
+  if (p->math_mode == SS_MATH_MIXED && st != 4 && st != 7)
+    return fail(SS_EINVAL, "SS_MATH_MIXED is available for the observe and fused stage masks%s");
   const int64_t nd = t ? t->blob_bytes / 8 : 0;
   if (t && (t->blob_bytes % 16 != 0)) return fail(SS_EINVAL, "blob_bytes must be a multiple of 16%s");
   if (st & SS_STAGE_GENERATE) {

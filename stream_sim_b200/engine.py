@@ -226,7 +226,7 @@ class StarEngine:
     def __init__(self, stream=None, survey=None, frame=None, device=None, bands=("r", "g"),
                  nside=4096, dust_correction=True, perfect_galstarsep=False,
                  detection_mag_cut=("g",), nest=False, hist=None, cdf_steps=1e5,
-                 grid_table=True):
+                 grid_table=True, math="f64"):
         torch = _torch()
         self.lib = _lib.load()
         self.device = require_device(device)
@@ -239,6 +239,9 @@ class StarEngine:
         packer = BlobPacker()
         p = self.params
         self._grid_table = bool(grid_table)
+        if math not in ("f64", "mixed"):
+            raise ValueError("math must be 'f64' or 'mixed'")
+        self.params.math_mode = _lib.MATH_MIXED if math == "mixed" else _lib.MATH_F64
         if stream is not None:
             self._describe_stream(stream, packer, int(cdf_steps))
         self.set_frame(frame)

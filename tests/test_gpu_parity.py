@@ -176,6 +176,43 @@ def test_fp32_output_mode(torch_cuda):
         assert_close(b[k].cpu().numpy().astype(float), a[k].cpu().numpy(), 1e-6, 1e-6, k)
 
 
+def test_mixed_precision_mode(torch_cuda):
+    """SS_MATH_MIXED: fp32 transcendentals with double fallback near decision
+    thresholds.  Under injected draws pixel indices and both flags are identical to
+    the fp64 path (hence to the reference), positions are untouched, magnitudes and
+    errors agree to 1e-5 relative (north-star bar for fp64 outputs)."""
+    n, seed = 1 << 20, 4242
+    exact, _ = _fused_engine("pal5", perfect_galstarsep=True)
+    mixed, _ = _fused_engine("pal5", perfect_galstarsep=True, math="mixed")
+    d = oracle.device_draws(seed, 0, n)
+    inj = {k: d[k] for k in ("u_phi1", "z_phi2", "u_dist", "u_mass", "z_r", "z_g", "u_det", "u_det2")}
+    a = exact.generate_observe(n, draws=inj, pix=True)
+    b = mixed.generate_observe(n, draws=inj, pix=True)
+    for k in ("pix", "flag_observed", "flag_perfect_galstarsep", "phi1", "phi2", "dist", "ra", "dec",
+              "mag_g", "mag_r"):
+        assert torch_cuda.equal(a[k].view(torch_cuda.uint8), b[k].view(torch_cuda.uint8)), k
+    for k in ("mag_g_obs", "mag_r_obs", "magerr_g", "magerr_r"):
+        assert_close(b[k].cpu().numpy(), a[k].cpu().numpy(), 1e-5, 0, k)
+    ref = _oracle_fused("pal5", d, perfect_galstarsep=True)
+    assert np.array_equal(b["pix"].cpu().numpy(), ref["pix"])
+    assert np.array_equal(b["flag_observed"].cpu().numpy().astype(bool), ref["flag_observed"])
+    # free-running (its own fp32 Box-Muller): same distributions
+    fa = exact.generate_observe(n, seed=seed)
+    fb = mixed.generate_observe(n, seed=seed)
+    pa, pb = float(fa["flag_observed"].float().mean()), float(fb["flag_observed"].float().mean())
+    assert abs(pa - pb) < 5 * np.sqrt(pa * (1 - pa) / n) + 1e-4
+    assert torch_cuda.equal(fa["phi1"], fb["phi1"])
+    for k in ("phi2", "mag_g_obs", "magerr_r"):
+        x, y = fa[k].cpu().numpy(), fb[k].cpu().numpy()
+        ok = ~(np.isnan(x) | np.isnan(y))
+        # same uniforms behind both: per-star values agree to fp32 round-off of the normals
+        assert np.median(np.abs(x[ok] - y[ok])) < 1e-5, k
+        assert np.quantile(np.abs(x[ok] - y[ok]), 0.99) < 1e-4, k
+        if k != "magerr_r":          # magerr has point masses (e.g. 10.000001): no KS
+            dks, crit = _ks(x[~np.isnan(x)][:200000], np.sort(y[~np.isnan(y)][:200000]))
+            assert dks < crit, k
+
+
 def test_host_buffer_entry_equals_device_entry(torch_cuda):
     n, chunk = 300000, 1 << 16
     eng, _ = _fused_engine("pal5")
