@@ -53,7 +53,11 @@ def ncu_traffic(dtype):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled during the timed region.  The
+    sampler is started before the warm-up (nvidia-smi takes a while to start) and
+    every row is time-stamped on arrival; stop(t0, t1) keeps the rows that fall
+    inside the timed window, widened to the neighbouring samples if the window was
+    shorter than a few sampling periods."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -74,19 +78,25 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0, t1):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        pad = 0.0
+        rows = [r for t, r in self.rows if t0 <= t <= t1]
+        while len(rows) < 3 and pad < 0.5:          # short region: include the neighbours
+            pad += 0.05
+            rows = [r for t, r in self.rows if t0 - pad <= t <= t1 + pad]
         sm, mx, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -95,12 +105,9 @@ class ClockSampler:
                         reasons.add(nm)
             except Exception:
                 continue
-        # the sampler also sees the idle head/tail of the region: use the upper half
-        sm_sorted = sorted(sm)
-        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
-        return {"sm_mhz": float(np.median(load)) if load else None,
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window_pad_s": pad}
 
 
 # ------------------------------------------------------------------ CPU arm
@@ -248,16 +255,16 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for k in range(args.warmup):
-        step(k)
-    barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-        time.sleep(0.3)
+    for k in range(args.warmup):
+        step(k)
+    barrier()
     # ---- timed region: exactly K steps; one star-kernel launch per step
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 2)]
     barrier()
+    t_wall0 = time.time()
     ev[0].record()
     for k in range(args.steps):
         ev[2 + 2 * k].record()
@@ -267,9 +274,10 @@ def run_gpu(args):
         ssd.reduce_counters(counters)
     ev[1].record()
     barrier()
+    t_wall1 = time.time()
     total_ms = ssd.max_over_ranks(ev[0].elapsed_time(ev[1]), device)
     kernel_ms = float(np.mean([ev[2 + 2 * k].elapsed_time(ev[3 + 2 * k]) for k in range(args.steps)]))
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     value = world * n * args.steps / (total_ms * 1e-3)
     summary = eng.summarize(counters)
 
