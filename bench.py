@@ -383,7 +383,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--stars", type=int, default=1 << 26, help="stars per step per GPU")
+    ap.add_argument("--stars", type=int, default=100_000_000,
+                    help="stars per step per GPU (BASELINE config 4: 1e8 stars)")
     ap.add_argument("--e2e-stars", type=int, default=1 << 24)
     ap.add_argument("--dtype", choices=("f64", "f32"), default="f64")
     ap.add_argument("--seed", type=int, default=12345)

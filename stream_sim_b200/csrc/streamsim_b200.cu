@@ -860,9 +860,9 @@ int ss_launch_info(int64_t blob_bytes, uint64_t n, int32_t* smem_bytes, int32_t*
 int ss_run(uint32_t stages, const SSParams* p, const SSTables* t, const SSMaps* m,
            const SSCatalog* in, const SSDraws* d, const SSOut* out, uint64_t n,
            uint64_t star_offset, uint64_t seed, void* stream) {
+  if (n == 0) return SS_OK;   // nothing to do (empty arrays may legitimately be NULL)
   int rc = validate(stages, p, t, m, in, out);
   if (rc) return rc;
-  if (n == 0) return SS_OK;
   DevInfo dev;
   if ((rc = device_info(dev))) return rc;
   KArgs a;

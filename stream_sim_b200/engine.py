@@ -538,6 +538,8 @@ class StarEngine:
     def run(self, stages, n, out, catalog=None, draws=None, seed=0, offset=0, counters=None,
             dtype="f64"):
         """Launch ``stages`` for ``n`` stars into the column tensors of ``out``."""
+        if int(n) == 0:
+            return out
         hold = []
         cat = _lib.SSCatalog()
         if catalog:

@@ -313,6 +313,77 @@ def test_free_running_magnitude_colour_ks(torch_cuda):
         assert d < crit, f"KS {what}: D={d:.4f} crit={crit:.4f}"
 
 
+# ------------------------------------------------------------------ more configurations
+def test_large_global_offsets(torch_cuda):
+    """Star indices beyond 2^32 (the high word of the Philox counter) -- the range a
+    1e11-star sharded run reaches."""
+    n, seed, offset = 50000, 5, (1 << 35) + 12345
+    eng, _ = _fused_engine("pal5")
+    out = eng.generate_observe(n, seed=seed, offset=offset, pix=True)
+    ref = _oracle_fused("pal5", oracle.device_draws(seed, offset, n))
+    assert np.array_equal(out["pix"].cpu().numpy(), ref["pix"])
+    assert np.array_equal(out["flag_observed"].cpu().numpy().astype(bool), ref["flag_observed"])
+    assert_close(out["mag_r_obs"].cpu().numpy(), ref["mag_r_obs"], RTOL, 1e-9, "mag_r_obs")
+    lo = eng.generate_observe(n, seed=seed, offset=12345)
+    assert not torch_cuda.equal(lo["phi1"], out["phi1"])
+
+
+def test_single_band_and_nested_maps(torch_cuda):
+    """bands=['r'] only (reference observed.py:154-258: g is then ignored, including its
+    SNR cut) and NESTED-ordered maps give the same answers as the oracle / the RING run."""
+    from stream_sim_b200 import healpix as hp
+    from stream_sim_b200.engine import StarEngine
+    from stream_sim_b200.surveys import Survey
+    n, seed = 100000, 17
+    full, _ = _fused_engine("pal5")
+    base = full.generate_observe(n, seed=seed)
+    cat = {k: base[k] for k in ("ra", "dec", "mag_g", "mag_r")}
+    sv = Survey.synthetic(128, 512)
+    only_r = StarEngine(survey=sv, bands=("r",))
+    got = only_r.observe(dict(ra=cat["ra"], dec=cat["dec"], mag_r=cat["mag_r"]), seed=seed)
+    assert set(got) == {"mag_r_obs", "magerr_r", "flag_observed"}
+    d = oracle.device_draws(seed, 0, n)
+    ref = oracle.observe(oracle_survey(), cat["ra"].cpu().numpy(), cat["dec"].cpu().numpy(),
+                         cat["mag_g"].cpu().numpy(), cat["mag_r"].cpu().numpy(), d, bands=("r",))
+    assert np.array_equal(got["flag_observed"].cpu().numpy().astype(bool), ref["flag_observed"])
+    assert_close(got["mag_r_obs"].cpu().numpy(), ref["mag_r_obs"], RTOL, 1e-9, "mag_r_obs")
+    assert int(got["flag_observed"].sum()) > int(base["flag_observed"].sum())   # no g cuts
+    # NESTED maps
+    nest_sv = Survey.synthetic(128, 512)
+    nest_sv.ebv_map = hp.reorder_ring_to_nest(sv.ebv_map)
+    nest_sv.maglim_maps = {b: hp.reorder_ring_to_nest(m) for b, m in sv.maglim_maps.items()}
+    ring_out = StarEngine(survey=sv).observe(cat, seed=seed, pix=True)
+    nest_out = StarEngine(survey=nest_sv, nest=True).observe(cat, seed=seed, pix=True)
+    for k in ("mag_g_obs", "mag_r_obs", "magerr_g", "magerr_r", "flag_observed"):
+        assert torch_cuda.equal(ring_out[k].view(torch_cuda.uint8), nest_out[k].view(torch_cuda.uint8)), k
+    assert np.array_equal(hp.ring2nest(4096, ring_out["pix"].cpu().numpy()),
+                          nest_out["pix"].cpu().numpy())
+
+
+def test_bad_inputs_raise_like_the_reference(torch_cuda):
+    import pandas as pd
+    from stream_sim_b200.observed import StreamInjector
+    from stream_sim_b200.surveys import Survey
+    inj = StreamInjector(Survey.synthetic(16, 16))
+    good = pd.DataFrame(dict(ra=[10.0, 20.0], dec=[-5.0, 5.0], mag_g=[22.0, 23.0], mag_r=[21.5, 22.5]))
+    assert len(inj.inject(good, seed=1, verbose=False)) == 2
+    empty = inj.inject(good.iloc[:0], seed=1, verbose=False)
+    assert len(empty) == 0 and "flag_observed" in empty.columns
+    bad = good.copy()
+    bad.loc[0, "dec"] = 95.0                               # healpy: THETA out of range
+    with pytest.raises(ValueError, match="THETA is out of range"):
+        inj.inject(bad, seed=1, verbose=False)
+    bad.loc[0, "dec"] = np.nan
+    with pytest.raises(ValueError, match="THETA is out of range"):
+        inj.inject(bad, seed=1, verbose=False)
+    nanmag = good.copy()
+    nanmag.loc[1, "mag_r"] = np.nan                        # propagates: BAD_MAG, not observed
+    res = inj.inject(nanmag, seed=1, verbose=False)
+    assert res["mag_r_obs"][1] == "BAD_MAG" and not res["flag_observed"][1]
+    with pytest.raises(ValueError, match="survey must be a string or Survey instance"):
+        StreamInjector(3)
+
+
 # ------------------------------------------------------------------ edge cases
 def test_empty_and_tiny_inputs(torch_cuda):
     eng, _ = _fused_engine("toy1")
