@@ -27,8 +27,6 @@ COLUMNS_FLOAT = ("phi1", "phi2", "dist", "mag_g", "mag_r", "ra", "dec",
                  "mag_g_obs", "mag_r_obs", "magerr_g", "magerr_r")
 GENERATE_COLUMNS = ("phi1", "phi2", "dist", "mag_g", "mag_r")
 ROTATE_COLUMNS = ("ra", "dec")
-OBSERVE_COLUMNS = ("mag_g_obs", "mag_r_obs", "magerr_g", "magerr_r", "flag_observed",
-                   "flag_perfect_galstarsep")
 SNR_MIN = 5.0            # reference observed.py:267
 CDF_GUIDE = 8192
 IMF_GUIDE = 4096

@@ -348,12 +348,6 @@ class StreamInjector:
         return mask_map
 
     # ------------------------------------------------------------------ pieces of inject
-    def _piece_engine(self, band, device=None):
-        bands = tuple(dict.fromkeys(("r", band)))      # 'r' is mandatory for the kernel
-        return self._engine(bands, 4096, False, True, (), device=device) \
-            if getattr(self.survey, "efficiency_detection", None) is not None \
-            else self._engine(bands, 4096, False, False, (), device=device)
-
     def sample_measured_magnitudes(self, mag_true, mag_err, **kwargs):
         """Noisy magnitudes from flux-space Gaussian noise (reference :863-904);
         "BAD_MAG" where the noisy flux is not positive.  Host arithmetic on the

@@ -46,7 +46,6 @@ def test_generate_isochrone_matches_oracle(torch_cuda):
     cfg = stream_config("pal5")
     n = 1 << 16
     d = oracle.device_draws(7, 0, n)
-    d["u_dist"] = d["u_dist"]
     df = StreamModel(cfg).sample(n, draws=dict(u_phi1=d["u_phi1"], z_phi2=d["z_phi2"],
                                                 u_dist=d["u_dist"], u_mass=d["u_mass"]))
     ref = oracle.generate(cfg, d, isochrone_table())
