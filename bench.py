@@ -238,7 +238,7 @@ def run_gpu(args):
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
-    eng, survey = build_engine(device, NSIDE)
+    eng, survey = build_engine(device, NSIDE, math=args.math)
     n = args.stars
     dtype = args.dtype
     out = eng.allocate(n, COLUMNS, dtype)
@@ -342,7 +342,8 @@ def run_gpu(args):
     line = {
         "metric": "observed stars/sec", "value": value, "unit": "stars/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": dtype if args.math == "f64" else dtype + " storage, mixed f32/f64 math",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "stars_per_step_per_gpu": n, "nside": NSIDE,
                    "stream": "config/pal5_config.yaml + synthetic isochrone",
@@ -391,6 +392,8 @@ def main():
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-mixed", action="store_true", help="skip the mixed-precision leg")
+    ap.add_argument("--math", choices=("f64", "mixed"), default="f64",
+                    help="arithmetic of the main leg (default f64; 'mixed' is for profiling)")
     ap.add_argument("--no-e2e", action="store_true",
                     help="profiling runs: shrink the end-to-end leg to a token size")
     args = ap.parse_args()

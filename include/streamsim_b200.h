@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SS_ABI_VERSION 6
+#define SS_ABI_VERSION 7
 
 /* error codes */
 #define SS_OK 0
@@ -190,10 +190,14 @@ typedef struct SSTables {
   const int32_t* cdf_perm;   /* [cdf_n] original index of sorted entry j; NULL if identity */
   const double* grid;        /* [cdf_n] explicit phi1 grid, or NULL = start + j*step */
   /* SS_DENSITY_GRID: rows[cdf_n][8] = (thr, x, centre, spread, dm_centre, dm_spread,
-   * sin(radians x), cos(radians x)); thr[k] = smallest u with sample index > k.
-   * lut[g] = sample index at u = g/grid_lut_n, g = 0..grid_lut_n. */
+   * sin(radians x), cos(radians x)); thr[k] = smallest u with sample index > k
+   * (thr[cdf_n-1] = +inf), also stored compactly in grid_thr[cdf_n].
+   * grid_lut[grid_lut_n][2 doubles]: bucket b = [b, b+1)/grid_lut_n of u ->
+   * (int32 lo | int32 k << 32 as the bits of the first double, thr[lo] as the second):
+   * lo = sample index at the bucket's left edge, k = thresholds inside the bucket. */
   const double* grid_rows;
-  const int32_t* grid_lut;
+  const double* grid_lut;
+  const double* grid_thr;
 } SSTables;
 
 typedef struct SSMaps {

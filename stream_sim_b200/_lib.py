@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 # ---- constants mirrored from the header
 STAGE_GENERATE, STAGE_ROTATE, STAGE_OBSERVE = 1, 2, 4
@@ -65,7 +65,7 @@ class SSParams(C.Structure):
 
 class SSTables(C.Structure):
     _fields_ = [("blob", _vp), ("blob_bytes", _i64), ("cdf_pairs", _vp), ("cdf_perm", _vp),
-                ("grid", _vp), ("grid_rows", _vp), ("grid_lut", _vp)]
+                ("grid", _vp), ("grid_rows", _vp), ("grid_lut", _vp), ("grid_thr", _vp)]
 
 
 class SSMaps(C.Structure):

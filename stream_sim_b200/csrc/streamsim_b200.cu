@@ -162,15 +162,27 @@ __device__ __forceinline__ bool grid_sample(const KArgs& a, double u, GridRow& r
   } else if (u >= 1.0) {
     idx = n - 1;
   } else {
-    const int g = (int)(u * (double)p.grid_lut_n);
-    int lo = __ldg(&a.t.grid_lut[g]), hi = __ldg(&a.t.grid_lut[g + 1]);
-    // first idx in [lo, hi] with u < thr[idx]
-    while (hi - lo > 2) {
-      const int mid = (lo + hi) >> 1;
-      if (u >= __ldg(&rows[4 * (size_t)mid].x)) lo = mid + 1; else hi = mid;
+    // One 16-byte table entry per bucket of u: (first index lo, number k of thresholds
+    // inside the bucket, thr[lo]).  For k <= 1 (82 % of the stars at 2^17 buckets) the
+    // index costs ONE round trip and no loop; otherwise a position-proportional guess
+    // keeps the warp-divergent fix-up loops to one or two trips.  (Measured: 2^17 buckets
+    // -- a 2 MB table that partly lives in L1 -- beat both 2^15 and 2^20.)
+    const double fb = u * (double)p.grid_lut_n;
+    const int b = (int)fb;
+    const double2 e = __ldg(&reinterpret_cast<const double2*>(a.t.grid_lut)[b]);
+    const long long packed = __double_as_longlong(e.x);
+    const int lo = (int)(packed & 0xffffffffLL), k = (int)(packed >> 32);
+    if (k <= 1) {
+      idx = lo + ((k == 1 && u >= e.y) ? 1 : 0);
+    } else {
+      // thresholds thr[lo .. lo+k-1] lie in this bucket: guess by position, then fix up
+      const double* __restrict__ thr = a.t.grid_thr;
+      int j = lo + (int)((fb - (double)b) * (double)k);   // candidate: first idx with u < thr[idx]
+      const int hi = lo + k;
+      while (j > lo && u < __ldg(&thr[j - 1])) --j;
+      while (j < hi && u >= __ldg(&thr[j])) ++j;
+      idx = j;
     }
-    while (lo < hi && u >= __ldg(&rows[4 * (size_t)lo].x)) ++lo;
-    idx = lo;
   }
   const double2 r0 = __ldg(&rows[4 * (size_t)idx]), r1 = __ldg(&rows[4 * (size_t)idx + 1]);
   const double2 r2 = __ldg(&rows[4 * (size_t)idx + 2]), r3 = __ldg(&rows[4 * (size_t)idx + 3]);
@@ -227,7 +239,13 @@ __device__ __forceinline__ void iso_sample(const SSParams& p, const double* __re
   if (p.imf_guide_n > 0 && u >= 0.0 && u < 1.0) {
     // guide[g] = last cdf entry <= g/G <= u: short forward scan
     const int32_t* guide = itab + 2 * p.imf_guide_off;
-    j = guide[(int)(u * (double)p.imf_guide_n)];
+    const double fb = u * (double)p.imf_guide_n;
+    const int b = (int)fb;
+    const int lo = guide[b], hi = guide[b + 1];
+    // the CDF is smooth: start from the position-proportional guess inside the bucket so
+    // that the (warp-divergent) fix-up loops run once or twice instead of hi-lo times
+    j = lo + (int)((fb - (double)b) * (double)(hi - lo));
+    while (j > lo && cdf[j] > u) --j;
     while (j + 1 < n && cdf[j + 1] <= u) ++j;
   } else {
     j = ss::search_le(cdf, 0, n, u);
@@ -544,6 +562,13 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
             good = t_f > 0.0f;
             if (good) mobs = m_true - (double)(0.75257499f * __log2f(t_f));   // 2.5 log10 t
             done = true;
+          } else if (loge != loge || zf != zf) {
+            // unseen pixel (NaN depth) or NaN draw: the answer is NaN / BAD_MAG in any
+            // precision -- do not send 2 % of the stars (and half of the warps) down the
+            // double path
+            err = (loge != loge) ? loge : (double)err_f;
+            good = false;
+            done = true;
           }
         }
         if (!done) {
@@ -776,8 +801,8 @@ int validate(uint32_t st, const SSParams* p, const SSTables* t, const SSMaps* m,
       if ((rc = check_func(p->dist_spread, nd, "distance_modulus.spread"))) return rc;
     }
     if (p->density_kind == SS_DENSITY_GRID) {
-      if (!t->grid_rows || !t->grid_lut || p->cdf_n < 2 || p->grid_lut_n < 1)
-        return fail(SS_EINVAL, "grid density needs grid_rows and grid_lut%s");
+      if (!t->grid_rows || !t->grid_lut || !t->grid_thr || p->cdf_n < 2 || p->grid_lut_n < 1)
+        return fail(SS_EINVAL, "grid density needs grid_rows, grid_lut and grid_thr%s");
     }
     if (p->density_kind == SS_DENSITY_INVCDF) {
       if (!t->cdf_pairs || p->cdf_n < 2) return fail(SS_EINVAL, "inverse-CDF density needs cdf_pairs%s");

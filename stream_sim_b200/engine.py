@@ -30,7 +30,7 @@ ROTATE_COLUMNS = ("ra", "dec")
 SNR_MIN = 5.0            # reference observed.py:267
 CDF_GUIDE = 8192
 IMF_GUIDE = 4096
-GRID_LUT = 1 << 17
+GRID_LUT = 1 << 17     # measured: 2^17 (2 MB, partly L1-resident) beats 2^15..2^20
 
 
 def _torch():
@@ -95,7 +95,7 @@ class BlobPacker:
         span = xs[-1] - xs[0]
         if n < 8 or not np.isfinite(span) or span <= 0:
             return dict(g_n=0, g_off=0, g_x0=0.0, g_inv=0.0)
-        g_n = 1 << int(np.ceil(np.log2(1.5 * n)))
+        g_n = 1 << int(np.ceil(np.log2((4.0 if n <= 512 else 1.5) * n)))
         inv = g_n / span
         edges = xs[0] + np.arange(g_n) / inv
         guide = np.maximum(np.searchsorted(xs, edges, side="right") - 1, 0).astype(np.int32)
@@ -366,17 +366,24 @@ class StarEngine:
         rad = np.radians(xg)
         rows = np.stack([np.concatenate([thr, [np.inf]]), xg, c, s, dc, ds, np.sin(rad),
                          np.cos(rad)], axis=1)
-        lut = np.searchsorted(thr, np.arange(GRID_LUT + 1) / GRID_LUT, side="right")
+        thr_full = np.concatenate([thr, [np.inf]])
+        edges = np.searchsorted(thr, np.arange(GRID_LUT + 1) / GRID_LUT, side="right")
+        lo, k = edges[:-1].astype(np.int64), np.diff(edges).astype(np.int64)
+        lut = np.empty((GRID_LUT, 2), dtype=np.float64)
+        lut[:, 0] = (lo | (k << 32)).view(np.float64)          # two int32 in one double
+        lut[:, 1] = thr_full[lo]
         self.grid_rows = torch.from_numpy(np.ascontiguousarray(rows, dtype=np.float64)).to(self.device)
-        self.grid_lut = torch.from_numpy(lut.astype(np.int32)).to(self.device)
+        self.grid_lut = torch.from_numpy(lut).to(self.device)
+        self.grid_thr = torch.from_numpy(thr_full).to(self.device)
         self.tables.grid_rows = self.grid_rows.data_ptr()
         self.tables.grid_lut = self.grid_lut.data_ptr()
+        self.tables.grid_thr = self.grid_thr.data_ptr()
         self.params.grid_lut_n = GRID_LUT
         self.params.density_kind = _lib.DENSITY_GRID
 
     def model_tensors(self):
         """Device tensors that make up the model/survey tables (not the maps)."""
-        names = ("blob", "cdf_pairs", "cdf_perm", "grid", "grid_rows", "grid_lut")
+        names = ("blob", "cdf_pairs", "cdf_perm", "grid", "grid_rows", "grid_lut", "grid_thr")
         return [getattr(self, k) for k in names if getattr(self, k, None) is not None]
 
     # ---- rotate
