@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SS_ABI_VERSION 7
+#define SS_ABI_VERSION 8
 
 /* error codes */
 #define SS_OK 0
@@ -84,21 +84,33 @@ extern "C" {
 #define SS_DTYPE_F32 1
 
 /* Philox4x32-10 draw blocks: counter = (star_lo, star_hi, block, 0),
- * key = (seed_lo, seed_hi).  Each block yields two 52-bit uniforms (U0,U1)
- * from the word pairs (w0,w1) and (w2,w3): U = ((w_even >> 12) * 2^32 + w_odd) * 2^-52:
- *   block 0: U0 = u_phi1, U1 = u_mass
- *   block 1: Gaussian samplers use Box-Muller(U0,U1) -> (z_phi2, z_dist);
- *            Uniform samplers use U0 for phi2 and U1 for dist
- *   block 2: Box-Muller(U0,U1) -> (z_r, z_g)   flux noise, r then g
- *   block 3: U0 = u_det (completeness), U1 = u_det2 (detection-only)
- *   block 4: Box-Muller(U0,U1).first -> z_phi1 (Gaussian density only)
- * A star's draws depend only on (seed, global star index): any sharding of the
- * index range over launches or GPUs gives identical per-star results. */
+ * key = (seed_lo, seed_hi), output words (w0,w1,w2,w3).
+ *   U52(a,b) = ((a >> 12) * 2^32 + b) * 2^-52   (52-bit uniform in [0,1))
+ *   U32(a)   = a * 2^-32
+ *   BM32(a,b): fp32 Box-Muller, radius from y = (a+0.5)/2^32, angle 2*pi*b/2^32
+ *   block 0: u_phi1 = U52(w0,w1), u_mass = U52(w2,w3)
+ *   block 1: (z_phi2, z_dist) = BM32(w0,w1)  [Uniform samplers: U32(w0), U32(w1)],
+ *            (z_r, z_g) = BM32(w2,w3)        flux noise
+ *   block 2: u_det = U52(w0,w1) (completeness), u_det2 = U52(w2,w3) (detection-only)
+ *   block 3: z_phi1 = BM32(w0,w1).first      (Gaussian density only)
+ * The normals are random draws, generated in fp32 like cuRAND's curand_normal;
+ * everything computed from them is double.  A star's draws depend only on
+ * (seed, global star index): any sharding of the index range over launches or
+ * GPUs gives identical per-star results.  SSOut.draws_out exports the draws used. */
 #define SS_DRAW_BLOCK_POS 0
-#define SS_DRAW_BLOCK_TRACK 1
-#define SS_DRAW_BLOCK_FLUX 2
-#define SS_DRAW_BLOCK_DETECT 3
-#define SS_DRAW_BLOCK_DENSITY_Z 4
+#define SS_DRAW_BLOCK_NORMAL 1
+#define SS_DRAW_BLOCK_DETECT 2
+#define SS_DRAW_BLOCK_DENSITY_Z 3
+/* rows of SSOut.draws_out */
+#define SS_DRAW_U_PHI1 0
+#define SS_DRAW_N_PHI2 1
+#define SS_DRAW_N_DIST 2
+#define SS_DRAW_U_MASS 3
+#define SS_DRAW_Z_G 4
+#define SS_DRAW_Z_R 5
+#define SS_DRAW_U_DET 6
+#define SS_DRAW_U_DET2 7
+#define SS_N_DRAWS 8
 
 /* counters written (atomically accumulated) into SSOut.counters */
 #define SS_CNT_TOTAL 0
@@ -240,6 +252,7 @@ typedef struct SSOut {
   uint8_t* flag_perfect;
   int64_t* pix;              /* ang2pix at nside_pix                             */
   unsigned long long* counters; /* [SS_COUNTERS_LEN], accumulated, or NULL       */
+  double* draws_out;         /* [SS_N_DRAWS][n] the draws actually used, or NULL  */
 } SSOut;
 
 int ss_abi_version(void);

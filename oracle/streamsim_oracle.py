@@ -72,42 +72,57 @@ def _u52(a, b):
 
 
 def philox_block(seed, index, block):
-    """The pair of uniforms of draw-block ``block`` for global star ``index``.
+    """The four 32-bit words of draw-block ``block`` for global star ``index``.
 
     counter = (index_lo, index_hi, block, 0), key = (seed_lo, seed_hi) --
     the layout documented in include/streamsim_b200.h (SS_DRAW_BLOCK_*).
     """
     index = np.asarray(index, dtype=np.uint64)
     seed = int(seed) & 0xFFFFFFFFFFFFFFFF
-    w = philox4x32_10((index & _MASK32).astype(np.uint32),
-                      (index >> np.uint64(32)).astype(np.uint32),
-                      np.uint32(block), np.uint32(0),
-                      seed & 0xFFFFFFFF, seed >> 32)
-    return _u52(w[0], w[1]), _u52(w[2], w[3])
+    return philox4x32_10((index & _MASK32).astype(np.uint32),
+                         (index >> np.uint64(32)).astype(np.uint32),
+                         np.uint32(block), np.uint32(0),
+                         seed & 0xFFFFFFFF, seed >> 32)
 
 
-def box_muller(ua, ub):
-    """(ua, ub) uniforms -> two standard normals, the device's formula."""
-    r = np.sqrt(-2.0 * np.log(1.0 - ua))
-    ang = 2.0 * ub  # in units of pi
-    return r * np.cos(np.pi * ang), r * np.sin(np.pi * ang)
+def _u32(a):
+    return a.astype(np.float64) * (1.0 / 4294967296.0)
+
+
+def bm32(wa, wb):
+    """The device's fp32 Box-Muller from two 32-bit words, emulated with NumPy float32.
+    NOT bit-identical to the CUDA intrinsics (agrees to ~1e-6): tests that need the exact
+    normals read them back from the kernel (SSOut.draws_out) instead."""
+    f = np.float32
+    k = f(2.3283064365386963e-10)
+    y = (wa.astype(f) + f(0.5)) * k
+    c1 = ((~wa).astype(f) + f(0.5)) * k
+    series = -c1 * (f(1) + c1 * (f(0.5) + c1 * (f(0.33333334) + c1 * f(0.25))))
+    with np.errstate(divide="ignore"):
+        l = np.where(c1 < f(0.03), series, np.log(y)).astype(f)
+    r = np.sqrt(f(-2) * l)
+    ang = wb.astype(np.float64) * 4.6566128730773926e-10
+    return ((r * np.cos(np.pi * ang).astype(f)).astype(np.float64),
+            (r * np.sin(np.pi * ang).astype(f)).astype(np.float64))
 
 
 def device_draws(seed, start, n):
     """All per-star draws the kernel derives for stars [start, start+n).
 
-    Returns the dict accepted by :func:`generate` / :func:`observe`:
-    u_phi1, u_mass, u_phi2, u_dist (raw uniforms of block 1), z_phi2, z_dist,
-    z_r, z_g, u_det, u_det2.
+    Returns the dict accepted by :func:`generate` / :func:`observe`.  The uniforms
+    (u_phi1, u_mass, u_phi2, u_dist, u_det, u_det2) are exactly the device's; the
+    normals (z_phi2, z_dist, z_r, z_g) are the float32 emulation of :func:`bm32`.
     """
     idx = np.arange(start, start + n, dtype=np.uint64)
-    u_phi1, u_mass = philox_block(seed, idx, 0)
-    ua, ub = philox_block(seed, idx, 1)
-    z_phi2, z_dist = box_muller(ua, ub)
-    va, vb = philox_block(seed, idx, 2)
-    z_r, z_g = box_muller(va, vb)
-    u_det, u_det2 = philox_block(seed, idx, 3)
-    return dict(u_phi1=u_phi1, u_mass=u_mass, u_phi2=ua, u_dist=ub,
+    w = philox_block(seed, idx, 0)
+    u_phi1, u_mass = _u52(w[0], w[1]), _u52(w[2], w[3])
+    w = philox_block(seed, idx, 1)
+    z_phi2, z_dist = bm32(w[0], w[1])
+    z_r, z_g = bm32(w[2], w[3])
+    u_phi2, u_dist = _u32(w[0]), _u32(w[1])
+    w = philox_block(seed, idx, 2)
+    u_det, u_det2 = _u52(w[0], w[1]), _u52(w[2], w[3])
+    return dict(u_phi1=u_phi1, u_mass=u_mass, u_phi2=u_phi2, u_dist=u_dist,
                 z_phi2=z_phi2, z_dist=z_dist, z_r=z_r, z_g=z_g,
                 u_det=u_det, u_det2=u_det2)
 

@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 # ---- constants mirrored from the header
 STAGE_GENERATE, STAGE_ROTATE, STAGE_OBSERVE = 1, 2, 4
@@ -23,6 +23,8 @@ MATH_F64, MATH_MIXED = 0, 1
 (CNT_TOTAL, CNT_OBSERVED, CNT_PERFECT, CNT_BADMAG_G, CNT_BADMAG_R, CNT_UNSEEN, CNT_DOMAIN,
  CNT_BADCOORD, CNT_INSIDE) = range(9)
 N_COUNTERS, HIST_BINS, N_HIST = 16, 256, 5
+N_DRAWS = 8
+DRAW_NAMES = ("u_phi1", "n_phi2", "n_dist", "u_mass", "z_g", "z_r", "u_det", "u_det2")
 COUNTERS_LEN = N_COUNTERS + N_HIST * HIST_BINS
 HIST_NAMES = ("phi1", "phi2", "dist", "mag_g", "g_minus_r")
 
@@ -86,7 +88,7 @@ class SSOut(C.Structure):
     _fields_ = [("dtype", _i32), ("pad_", _i32), ("phi1", _vp), ("phi2", _vp), ("dist", _vp),
                 ("mag", _vp * 2), ("ra", _vp), ("dec", _vp), ("mag_obs", _vp * 2),
                 ("magerr", _vp * 2), ("flag_observed", _vp), ("flag_perfect", _vp),
-                ("pix", _vp), ("counters", _vp)]
+                ("pix", _vp), ("counters", _vp), ("draws_out", _vp)]
 
 
 _STRUCTS = (SSFunc, SSParams, SSTables, SSMaps, SSCatalog, SSDraws, SSOut)

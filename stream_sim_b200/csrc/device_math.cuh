@@ -32,33 +32,28 @@ __device__ __forceinline__ double u52(uint32_t a, uint32_t b) {
   return __hiloint2double((int)(0x3ff00000u | (a >> 12)), (int)b) - 1.0;
 }
 
-__device__ __forceinline__ void philox_pair(unsigned long long star, uint32_t block,
-                                            unsigned long long seed, double& u0, double& u1) {
-  uint4 c = make_uint4((uint32_t)star, (uint32_t)(star >> 32), block, 0u);
-  c = philox4x32_10(c, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  u0 = u52(c.x, c.y);
-  u1 = u52(c.z, c.w);
+__device__ __forceinline__ uint4 philox_block(unsigned long long star, uint32_t block,
+                                              unsigned long long seed) {
+  const uint4 c = make_uint4((uint32_t)star, (uint32_t)(star >> 32), block, 0u);
+  return philox4x32_10(c, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
 }
 
-__device__ __forceinline__ void box_muller(double ua, double ub, double& z0, double& z1) {
-  const double r = sqrt(-2.0 * log(1.0 - ua));
-  double s, c;
-  sincospi(2.0 * ub, &s, &c);
-  z0 = r * c;
-  z1 = r * s;
-}
+// one 32-bit word -> double in [0,1), exact
+__device__ __forceinline__ double u32(uint32_t w) { return (double)w * (1.0 / 4294967296.0); }
 
-// Box-Muller in fp32 (mixed-precision mode): the same two uniforms, single-precision
-// log / sqrt / sincos.  The radius uses a short series for small ua, where
-// log(1-ua) computed through log2 would lose relative accuracy.
-__device__ __forceinline__ void box_muller_f32(double ua, double ub, double& z0, double& z1) {
-  const float uf = (float)ua;
-  const float l_series = -uf * (1.0f + uf * (0.5f + uf * (0.33333334f + uf * 0.25f)));
-  const float l_log = __logf((float)(1.0 - ua));
-  const float l = (uf < 0.03f) ? l_series : l_log;
+// Box-Muller from two 32-bit words, evaluated in fp32 (like cuRAND's curand_normal): the
+// draw is a random number, not a quantity with a parity requirement, and everything
+// computed *from* it downstream stays in double.  y = (wa+0.5)/2^32 in (0,1) feeds the
+// radius; for y close to 1 the complement (~wa+0.5)/2^32 = 1-y is exact and a short
+// series replaces log(y), which would lose relative accuracy there.  |z| <= 6.7.
+__device__ __forceinline__ void bm32(uint32_t wa, uint32_t wb, double& z0, double& z1) {
+  const float y = ((float)wa + 0.5f) * 2.3283064365386963e-10f;
+  const float c1 = ((float)(~wa) + 0.5f) * 2.3283064365386963e-10f;
+  const float l_series = -c1 * (1.0f + c1 * (0.5f + c1 * (0.33333334f + c1 * 0.25f)));
+  const float l = (c1 < 0.03f) ? l_series : __logf(y);
   const float r = sqrtf(-2.0f * l);
   float s, c;
-  sincospif(2.0f * (float)ub, &s, &c);
+  sincospif((float)wb * 4.6566128730773926e-10f, &s, &c);   // angle/pi = 2*wb/2^32
   z0 = (double)(r * c);
   z1 = (double)(r * s);
 }

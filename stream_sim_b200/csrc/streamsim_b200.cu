@@ -310,6 +310,7 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
   const double* const in_phi1 = LEAN ? nullptr : a.in.phi1;
   const double* const in_phi2 = LEAN ? nullptr : a.in.phi2;
   const double* const in_dist = LEAN ? nullptr : a.in.dist;
+  double* const draws_out = LEAN ? nullptr : a.o.draws_out;
   const int density_kind = LEAN ? SS_DENSITY_GRID : p.density_kind;
   const bool has_dist = LEAN ? true : (p.has_dist != 0);
   const bool has_iso = LEAN ? true : (p.has_iso != 0);
@@ -354,7 +355,9 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
         u_phi1 = d_u_phi1[i];
         u_mass = has_iso ? d_u_mass[i] : 0.0;
       } else {
-        ss::philox_pair(gi, SS_DRAW_BLOCK_POS, a.seed, u_phi1, u_mass);
+        const uint4 w = ss::philox_block(gi, SS_DRAW_BLOCK_POS, a.seed);
+        u_phi1 = ss::u52(w.x, w.y);
+        u_mass = ss::u52(w.z, w.w);
         if (d_u_phi1) u_phi1 = d_u_phi1[i];
         if (d_u_mass) u_mass = d_u_mass[i];
       }
@@ -371,10 +374,9 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
       } else if (density_kind == SS_DENSITY_GAUSSIAN) {  // u_phi1 slot carries a normal draw
         double z = u_phi1;
         if (!d_u_phi1) {
-          double ua, ub, z1;
-          ss::philox_pair(gi, SS_DRAW_BLOCK_DENSITY_Z, a.seed, ua, ub);
-          if (MATH == SS_MATH_MIXED) ss::box_muller_f32(ua, ub, z, z1);
-          else ss::box_muller(ua, ub, z, z1);
+          double z1;
+          const uint4 w = ss::philox_block(gi, SS_DRAW_BLOCK_DENSITY_Z, a.seed);
+          ss::bm32(w.x, w.y, z, z1);
         }
         phi1 = __dadd_rn(__dmul_rn(z, p.density_hi), p.density_lo);
       } else {
@@ -386,19 +388,21 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
         n_phi2 = d_n_phi2[i];
         n_dist = has_dist ? d_n_dist[i] : 0.0;
       } else {
-        double ua, ub;
-        ss::philox_pair(gi, SS_DRAW_BLOCK_TRACK, a.seed, ua, ub);
+        const uint4 wn = ss::philox_block(gi, SS_DRAW_BLOCK_NORMAL, a.seed);
         const bool need_z = (p.track_sampler == SS_SAMPLER_GAUSSIAN) ||
                             (has_dist && p.dist_sampler == SS_SAMPLER_GAUSSIAN);
         double z0 = 0, z1 = 0;
-        if (need_z) {
-          if (MATH == SS_MATH_MIXED) ss::box_muller_f32(ua, ub, z0, z1);
-          else ss::box_muller(ua, ub, z0, z1);
-        }
-        n_phi2 = (p.track_sampler == SS_SAMPLER_GAUSSIAN) ? z0 : ua;
-        n_dist = (p.dist_sampler == SS_SAMPLER_GAUSSIAN) ? z1 : ub;
+        if (need_z) ss::bm32(wn.x, wn.y, z0, z1);
+        n_phi2 = (p.track_sampler == SS_SAMPLER_GAUSSIAN) ? z0 : ss::u32(wn.x);
+        n_dist = (p.dist_sampler == SS_SAMPLER_GAUSSIAN) ? z1 : ss::u32(wn.y);
         if (d_n_phi2) n_phi2 = d_n_phi2[i];
         if (d_n_dist) n_dist = d_n_dist[i];
+      }
+      if (draws_out) {
+        draws_out[SS_DRAW_U_PHI1 * a.n + i] = u_phi1;
+        draws_out[SS_DRAW_U_MASS * a.n + i] = u_mass;
+        draws_out[SS_DRAW_N_PHI2 * a.n + i] = n_phi2;
+        draws_out[SS_DRAW_N_DIST * a.n + i] = n_dist;
       }
       const double phi2_given = in_phi2 ? in_phi2[i] : ss::nan_d();
       if (phi2_given == phi2_given) {
@@ -507,10 +511,10 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
         z_g = d_z_g[i];
         z_r = d_z_r[i];
       } else {
-        double ua, ub;
-        ss::philox_pair(gi, SS_DRAW_BLOCK_FLUX, a.seed, ua, ub);
-        if (MATH == SS_MATH_MIXED) ss::box_muller_f32(ua, ub, z_r, z_g);
-        else ss::box_muller(ua, ub, z_r, z_g);
+        // recomputed rather than kept live since the generate stage: registers are the
+        // scarce resource of this kernel (measured +9 % over carrying the words across)
+        const uint4 wn = ss::philox_block(gi, SS_DRAW_BLOCK_NORMAL, a.seed);
+        ss::bm32(wn.z, wn.w, z_r, z_g);
         if (d_z_g) z_g = d_z_g[i];
         if (d_z_r) z_r = d_z_r[i];
       }
@@ -519,11 +523,19 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
         u_det = d_u_det[i];
         u_det2 = p.perfect_galstarsep ? d_u_det2[i] : 0.0;
       } else {
-        ss::philox_pair(gi, SS_DRAW_BLOCK_DETECT, a.seed, u_det, u_det2);
+        const uint4 w = ss::philox_block(gi, SS_DRAW_BLOCK_DETECT, a.seed);
+        u_det = ss::u52(w.x, w.y);
+        u_det2 = ss::u52(w.z, w.w);
         if (d_u_det) u_det = d_u_det[i];
         if (d_u_det2) u_det2 = d_u_det2[i];
       }
 
+      if (draws_out) {
+        draws_out[SS_DRAW_Z_G * a.n + i] = z_g;
+        draws_out[SS_DRAW_Z_R * a.n + i] = z_r;
+        draws_out[SS_DRAW_U_DET * a.n + i] = u_det;
+        draws_out[SS_DRAW_U_DET2 * a.n + i] = u_det2;
+      }
       bool valid = true, flag_c = false, flag_d = false, snr_ok = true, snr_r_ok = true;
 #pragma unroll
       for (int b = 0; b < 2; ++b) {
@@ -755,7 +767,7 @@ int launch_stage(uint32_t st, const KArgs& a, int smem, int grid, cudaStream_t s
                         a.p.has_iso && a.p.band_present[0] && a.p.band_present[1] &&
                         !d.u_phi1 && !d.u_mass && !d.n_phi2 && !d.n_dist && !d.z_flux[0] &&
                         !d.z_flux[1] && !d.u_det && !d.u_det2 && !a.in.phi1 && !a.in.phi2 &&
-                        !a.in.dist;
+                        !a.in.dist && !a.o.draws_out;
       if (a.p.math_mode == SS_MATH_MIXED)
         return lean ? launch_t<7, OutT, true, SS_MATH_MIXED>(a, smem, grid, s)
                     : launch_t<7, OutT, false, SS_MATH_MIXED>(a, smem, grid, s);

@@ -480,8 +480,9 @@ class StarEngine:
     def new_counters(self):
         return _torch().zeros(_lib.COUNTERS_LEN, dtype=_torch().int64, device=self.device)
 
-    def allocate(self, n, columns, dtype="f64", pix=False):
-        """Structure-of-arrays output buffers for ``columns``."""
+    def allocate(self, n, columns, dtype="f64", pix=False, draws=False):
+        """Structure-of-arrays output buffers for ``columns`` (``draws=True`` adds the
+        [8][n] export of the random draws the kernel used, rows ``_lib.DRAW_NAMES``)."""
         torch = _torch()
         ft = torch.float64 if dtype == "f64" else torch.float32
         out = {}
@@ -492,6 +493,9 @@ class StarEngine:
                 out[c] = torch.empty(n, dtype=torch.uint8, device=self.device)
         if pix:
             out["pix"] = torch.empty(n, dtype=torch.int64, device=self.device)
+        if draws:
+            out["draws"] = torch.full((_lib.N_DRAWS, n), float("nan"), dtype=torch.float64,
+                                      device=self.device)
         return out
 
     def _out_struct(self, out, counters, dtype):
@@ -506,6 +510,7 @@ class StarEngine:
         o.flag_observed = ptr("flag_observed")
         o.flag_perfect = ptr("flag_perfect_galstarsep")
         o.pix = ptr("pix")
+        o.draws_out = ptr("draws")
         o.counters = counters.data_ptr() if counters is not None else None
         return o
 
@@ -594,21 +599,21 @@ class StarEngine:
         return cols
 
     def observe(self, catalog, seed=0, offset=0, draws=None, counters=None, dtype="f64",
-                out=None, pix=False):
+                out=None, pix=False, export_draws=False):
         """catalog: dict with (ra, dec) or (phi1, phi2), and mag_g / mag_r."""
         has_radec = catalog.get("ra") is not None and catalog.get("dec") is not None
         n = len(catalog["ra"] if has_radec else catalog["phi1"])
         stages = _lib.STAGE_OBSERVE if has_radec else (_lib.STAGE_ROTATE | _lib.STAGE_OBSERVE)
         cols = self._observe_columns(pix) + ([] if has_radec else list(ROTATE_COLUMNS))
-        out = out if out is not None else self.allocate(n, cols, dtype, pix=pix)
+        out = out if out is not None else self.allocate(n, cols, dtype, pix=pix, draws=export_draws)
         return self.run(stages, n, out, catalog, draws, seed, offset, counters, dtype)
 
     def generate_observe(self, n, seed=0, offset=0, draws=None, counters=None, dtype="f64",
-                         out=None, pix=False, columns=None):
+                         out=None, pix=False, columns=None, export_draws=False):
         if out is None:
             cols = columns if columns is not None else (
                 list(GENERATE_COLUMNS) + list(ROTATE_COLUMNS) + self._observe_columns(pix))
-            out = self.allocate(n, cols, dtype, pix=pix)
+            out = self.allocate(n, cols, dtype, pix=pix, draws=export_draws)
         st = _lib.STAGE_GENERATE | _lib.STAGE_ROTATE | _lib.STAGE_OBSERVE
         return self.run(st, n, out, None, draws, seed, offset, counters, dtype)
 
@@ -676,6 +681,18 @@ class StarEngine:
         return out_host
 
     # ---- summaries
+    @staticmethod
+    def exported_draws(out, sampler_kinds=None):
+        """The ``draws`` export of a launch as the dict the oracle / ``draws=`` accept."""
+        d = out["draws"].cpu().numpy()
+        named = {k: d[i] for i, k in enumerate(_lib.DRAW_NAMES)}
+        res = dict(u_phi1=named["u_phi1"], u_mass=named["u_mass"], z_g=named["z_g"],
+                   z_r=named["z_r"], u_det=named["u_det"], u_det2=named["u_det2"])
+        # the track slots hold a normal or a uniform depending on the sampler
+        res["z_phi2"] = res["u_phi2"] = named["n_phi2"]
+        res["z_dist"] = res["u_dist"] = named["n_dist"]
+        return res
+
     @staticmethod
     def summarize(counters):
         """Counter tensor -> dict (one device->host copy)."""

@@ -121,19 +121,40 @@ def _oracle_fused(cfg_name, draws, compl_band="r", **kw):
                                    oracle_survey(compl_band), draws, **kw)
 
 
+def _check_draws_against_oracle(used, seed, offset, n):
+    """The draws exported by the kernel vs the oracle's derivation: uniforms are exact,
+    the fp32 Box-Muller normals agree with the NumPy float32 emulation to ~1e-6."""
+    ref = oracle.device_draws(seed, offset, n)
+    for k in ("u_phi1", "u_mass", "u_det", "u_det2"):
+        assert np.array_equal(used[k], ref[k]), k
+    for k in ("z_r", "z_g"):
+        assert np.abs(used[k] - ref[k]).max() < 5e-6, k
+    return ref
+
+
 @pytest.mark.parametrize("cfg_name,grid_table", [("toy1", True), ("pal5", True), ("pal5", False)])
 def test_fused_free_running_matches_oracle(torch_cuda, cfg_name, grid_table):
-    """Free-running (Philox on the device) fused generate->rotate->observe equals
-    the oracle fed with the same Philox-derived draws: pixel indices and flags
-    bit-exact, everything else to 1e-9."""
+    """Free-running (Philox on the device) fused generate->rotate->observe equals the
+    oracle fed with the draws the kernel used (exported through SSOut.draws_out, and
+    themselves checked against the oracle's Philox derivation): pixel indices and
+    flags bit-exact, everything else to 1e-9.  The production (LEAN) instantiation,
+    which cannot export draws, must produce the very same bytes."""
     n, seed, offset = 1 << 18, 12345, 1000
     eng, _ = _fused_engine(cfg_name, perfect_galstarsep=True, grid_table=grid_table)
     from stream_sim_b200 import _lib
     assert (eng.params.density_kind == _lib.DENSITY_GRID) == (grid_table and cfg_name == "pal5")
     cnt = eng.new_counters()
-    out = eng.generate_observe(n, seed=seed, offset=offset, counters=cnt, pix=True)
+    out = eng.generate_observe(n, seed=seed, offset=offset, counters=cnt, pix=True,
+                               export_draws=True)
     got = {k: v.cpu().numpy() for k, v in out.items()}
-    draws = oracle.device_draws(seed, offset, n)
+    draws = eng.exported_draws(out)
+    odraws = _check_draws_against_oracle(draws, seed, offset, n)
+    if cfg_name == "toy1":          # Gaussian track, Uniform distance modulus
+        assert np.abs(draws["z_phi2"] - odraws["z_phi2"]).max() < 5e-6
+        assert np.array_equal(draws["u_dist"], odraws["u_dist"])
+    lean = eng.generate_observe(n, seed=seed, offset=offset, pix=True)
+    for k, v in lean.items():
+        assert torch_cuda.equal(v.view(torch_cuda.uint8), out[k].view(torch_cuda.uint8)), k
     ref = _oracle_fused(cfg_name, draws, perfect_galstarsep=True)
     assert np.array_equal(got["phi1"], ref["phi1"])
     assert np.array_equal(got["pix"], ref["pix"]), "pixel indices"
@@ -148,6 +169,27 @@ def test_fused_free_running_matches_oracle(torch_cuda, cfg_name, grid_table):
     assert s["n_perfect_galstarsep"] == int(ref["flag_perfect_galstarsep"].sum())
     assert s["n_badmag_r"] == int(np.isnan(ref["mag_r_obs"]).sum())
     assert s["n_badmag_g"] == int(np.isnan(ref["mag_g_obs"]).sum())
+
+
+def test_device_normals_are_standard_normal(torch_cuda):
+    """The fp32 Box-Muller draws: KS against the exact normal CDF at 2 million draws per
+    slot, moments, independence of the pairs, and a populated 4-sigma tail."""
+    from scipy import stats
+    n = 1 << 21
+    eng, _ = _fused_engine("toy1")            # Gaussian track: z_phi2 is a normal
+    out = eng.generate_observe(n, seed=99, export_draws=True, columns=["flag_observed"])
+    d = eng.exported_draws(out)
+    for k in ("z_phi2", "z_r", "z_g"):
+        z = d[k]
+        assert stats.kstest(z, "norm").pvalue > 1e-3, k
+        assert abs(z.mean()) < 4 / np.sqrt(n) and abs(z.var() - 1) < 6 * np.sqrt(2 / n), k
+        assert abs(stats.kurtosis(z)) < 0.02, k
+        tail = (np.abs(z) > 4).mean()
+        assert 0.5 * 6.33e-5 < tail < 1.6 * 6.33e-5, (k, tail)
+    assert abs(np.corrcoef(d["z_r"], d["z_g"])[0, 1]) < 4 / np.sqrt(n)
+    assert abs(np.corrcoef(d["z_phi2"], d["z_r"])[0, 1]) < 4 / np.sqrt(n)
+    for k in ("u_phi1", "u_mass", "u_det"):
+        assert stats.kstest(d[k], "uniform").pvalue > 1e-3, k
 
 
 def test_shard_invariance_and_offsets(torch_cuda):
@@ -318,8 +360,10 @@ def test_large_global_offsets(torch_cuda):
     1e11-star sharded run reaches."""
     n, seed, offset = 50000, 5, (1 << 35) + 12345
     eng, _ = _fused_engine("pal5")
-    out = eng.generate_observe(n, seed=seed, offset=offset, pix=True)
-    ref = _oracle_fused("pal5", oracle.device_draws(seed, offset, n))
+    out = eng.generate_observe(n, seed=seed, offset=offset, pix=True, export_draws=True)
+    draws = eng.exported_draws(out)
+    _check_draws_against_oracle(draws, seed, offset, n)
+    ref = _oracle_fused("pal5", draws)
     assert np.array_equal(out["pix"].cpu().numpy(), ref["pix"])
     assert np.array_equal(out["flag_observed"].cpu().numpy().astype(bool), ref["flag_observed"])
     assert_close(out["mag_r_obs"].cpu().numpy(), ref["mag_r_obs"], RTOL, 1e-9, "mag_r_obs")
@@ -339,9 +383,10 @@ def test_single_band_and_nested_maps(torch_cuda):
     cat = {k: base[k] for k in ("ra", "dec", "mag_g", "mag_r")}
     sv = Survey.synthetic(128, 512)
     only_r = StarEngine(survey=sv, bands=("r",))
-    got = only_r.observe(dict(ra=cat["ra"], dec=cat["dec"], mag_r=cat["mag_r"]), seed=seed)
-    assert set(got) == {"mag_r_obs", "magerr_r", "flag_observed"}
-    d = oracle.device_draws(seed, 0, n)
+    got = only_r.observe(dict(ra=cat["ra"], dec=cat["dec"], mag_r=cat["mag_r"]), seed=seed,
+                         export_draws=True)
+    assert set(got) == {"mag_r_obs", "magerr_r", "flag_observed", "draws"}
+    d = only_r.exported_draws(got)
     ref = oracle.observe(oracle_survey(), cat["ra"].cpu().numpy(), cat["dec"].cpu().numpy(),
                          cat["mag_g"].cpu().numpy(), cat["mag_r"].cpu().numpy(), d, bands=("r",))
     assert np.array_equal(got["flag_observed"].cpu().numpy().astype(bool), ref["flag_observed"])
