@@ -740,11 +740,19 @@ int plan_launch(const DevInfo& d, int64_t blob_bytes, uint64_t n, int& smem, int
 
 template <uint32_t ST, typename OutT, bool LEAN = false, int MATH = SS_MATH_F64>
 int launch_t(const KArgs& a, int smem, int grid, cudaStream_t stream) {
-  static thread_local int configured_smem = -1;
+  // the opt-in dynamic shared-memory limit is a per-device, per-kernel attribute
+  static thread_local int configured_smem[64];
+  static thread_local bool init = false;
+  if (!init) {
+    for (int& v : configured_smem) v = -1;
+    init = true;
+  }
+  int dev = 0;
+  SS_CUDA(cudaGetDevice(&dev));
   auto kern = k_stars<ST, OutT, LEAN, MATH>;
-  if (smem > configured_smem) {
+  if (dev < 0 || dev >= 64 || smem > configured_smem[dev]) {
     SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured_smem = smem;
+    if (dev >= 0 && dev < 64) configured_smem[dev] = smem;
   }
   kern<<<grid, SS_BLOCK, smem, stream>>>(a);
   SS_CUDA(cudaGetLastError());

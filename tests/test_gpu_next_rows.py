@@ -205,6 +205,35 @@ def test_standalone_samplers_and_models():
     assert_close(mr, rr, 1e-9, 0, "mag_r")
 
 
+def test_tables_too_large_for_shared_memory():
+    """A 40000-knot track/density table (1.9 MB of tables) does not fit the 227 KB of shared
+    memory: the kernel then reads the blob from global memory.  Same answers."""
+    from stream_sim_b200.model import StreamModel
+    rng = np.random.default_rng(11)
+    xk = np.sort(rng.uniform(-10, 10, 40000))
+    xk[0], xk[-1] = -10.0, 10.0
+    cfg = dict(density=dict(type="Interpolation", xvals=list(xk), yvals=list(1.0 + 0.5 * np.sin(xk))),
+               track=dict(center=dict(type="Interpolation", xvals=list(xk), yvals=list(0.3 * np.cos(xk))),
+                          spread=dict(type="Interpolation", xvals=list(xk),
+                                      yvals=list(0.2 + 0.05 * np.sin(2 * xk))),
+                          sampler="Gaussian"),
+               distance_modulus=dict(center=dict(type="Line", slope=0.1, intercept=16.5),
+                                     spread=dict(type="Constant", value=0.05), sampler="Gaussian"))
+    n = 20000
+    d = oracle.device_draws(3, 0, n)
+    model = StreamModel(cfg)
+    eng = model.engine()
+    import ctypes as C
+    smem, grid, block = C.c_int32(), C.c_int32(), C.c_int32()
+    eng.lib.ss_launch_info(eng.blob.numel(), n, C.byref(smem), C.byref(grid), C.byref(block))
+    assert eng.blob.numel() > 227 * 1024 and smem.value == 0 and block.value == 1024
+    df = model.sample(n, draws=dict(u_phi1=d["u_phi1"], z_phi2=d["z_phi2"], z_dist=d["z_dist"]))
+    ref = oracle.generate(cfg, d)
+    assert np.array_equal(df["phi1"].to_numpy(), ref["phi1"])
+    assert_close(df["phi2"].to_numpy(), ref["phi2"], 1e-9, 1e-12, "phi2")
+    assert_close(df["dist"].to_numpy(dtype=float), ref["dist"], 1e-9, 0, "dist")
+
+
 def test_survey_getters_on_device(survey):
     sv = oracle_survey()
     rng = np.random.default_rng(4)
