@@ -300,6 +300,40 @@ def test_summary_only_mode_equals_full_run(torch_cuda):
     assert np.abs(s["hist_phi1"] - ref).sum() <= 4     # edge rounding only
 
 
+def test_full_size_properties(torch_cuda):
+    """BASELINE config 4 size (1e8 stars, nside-4096 maps generated on the device):
+    size-independent properties instead of a star-by-star oracle run --
+    idempotence (same seed, same counters), additivity over any sharding of the index
+    range (the multi-GPU contract), conservation (every star lands in the phi1
+    histogram; observed <= total), and agreement of the observed fraction with a
+    2^20-star launch that IS checked star by star elsewhere."""
+    from stream_sim_b200.engine import StarEngine
+    from stream_sim_b200.frames import GreatCircleFrame
+    from stream_sim_b200.model import StreamModel
+    from stream_sim_b200.surveys import Survey
+    from stream_sim_b200.synthetic import NOTEBOOK_ENDPOINTS
+    n, seed = 100_000_000, 2026
+    sv = Survey.synthetic(4096, 4096, device="cuda")
+    eng = StarEngine(stream=StreamModel(stream_config("pal5")), survey=sv,
+                     frame=GreatCircleFrame.from_endpoints(*NOTEBOOK_ENDPOINTS), hist=True)
+    whole = eng.run_summary(n, seed=seed, chunk=n)
+    again = eng.run_summary(n, seed=seed, chunk=n)
+    assert torch_cuda.equal(whole, again), "idempotence"
+    shards = eng.new_counters()
+    cuts = [0, 1, 12_500_000, 37_500_001, 50_000_000, 99_999_999, n]
+    for lo, hi in zip(cuts, cuts[1:]):
+        eng.generate_observe(hi - lo, seed=seed, offset=lo, counters=shards, out={})
+    assert torch_cuda.equal(whole, shards), "additivity over shards"
+    s = eng.summarize(whole)
+    assert s["n_total"] == n and s["hist_phi1"].sum() == n
+    assert 0 < s["n_observed"] < n and s["n_domain_error"] == 0 and s["n_bad_coord"] == 0
+    small = eng.summarize(eng.run_summary(1 << 20, seed=seed))
+    f_big, f_small = s["n_observed"] / n, small["n_observed"] / (1 << 20)
+    assert abs(f_big - f_small) < 5 * np.sqrt(f_small * (1 - f_small) / (1 << 20))
+    # unseen pixels: 2 % of the map, so ~2 % of the stars
+    assert abs(s["n_unseen"] / n - 0.02) < 0.004
+
+
 # ------------------------------------------------------------------ distributions
 def _ks(sample, ref_sorted):
     sample = np.sort(sample)
