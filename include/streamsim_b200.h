@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SS_ABI_VERSION 8
+#define SS_ABI_VERSION 9
 
 /* error codes */
 #define SS_OK 0
@@ -165,7 +165,8 @@ typedef struct SSParams {
   int32_t imf_guide_n;  /* power of two                                           */
   int32_t imf_guide_off;/* blob offset (in doubles) of int32 guide[imf_guide_n+1] */
   int32_t cdf_guide_off;/* blob offset (in doubles) of int32 guide[cdf_guide_n+1] */
-  int32_t pad0_;
+  int32_t iso_direct;   /* 1: mags(u) tabulated on the composite breakpoints (SSTables.iso_*);
+                           iso_n is then the number of composite rows, iso_lut_n the buckets */
   double imf_mass_lo, imf_mass_hi, imf_mass_step; /* np.linspace(lo,hi,imf_n)     */
   double iso_guide_x0, iso_guide_inv;
   /* ---- rotate: R rows = (origin, pole x origin, pole), ICRS -> stream frame */
@@ -192,7 +193,7 @@ typedef struct SSParams {
   int32_t grid_lut_n;       /* SS_DENSITY_GRID: buckets of the u -> index table   */
   double hist_lo[SS_N_HIST], hist_inv_width[SS_N_HIST];
   int32_t math_mode;        /* SS_MATH_*                                          */
-  int32_t pad2_;
+  int32_t iso_lut_n;        /* buckets of SSTables.iso_lut (iso_direct)           */
 } SSParams;
 
 typedef struct SSTables {
@@ -210,6 +211,12 @@ typedef struct SSTables {
   const double* grid_rows;
   const double* grid_lut;
   const double* grid_thr;
+  /* iso_direct: rows[iso_n][6] = (U_k, mag_g, dmag_g/du, mag_r, dmag_r/du, 0) on the union of
+   * the IMF-CDF knots and the isochrone knots mapped to u; thr[k] = U_{k+1} (last = +inf);
+   * lut[iso_lut_n][2] packed exactly like grid_lut. */
+  const double* iso_rows;
+  const double* iso_lut;
+  const double* iso_thr;
 } SSTables;
 
 typedef struct SSMaps {

@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 # ---- constants mirrored from the header
 STAGE_GENERATE, STAGE_ROTATE, STAGE_OBSERVE = 1, 2, 4
@@ -48,7 +48,7 @@ class SSParams(C.Structure):
         ("track_sampler", _i32), ("dist_sampler", _i32), ("has_dist", _i32), ("has_iso", _i32),
         ("iso_n", _i32), ("iso_mass_off", _i32), ("iso_mag_off", _i32 * 2),
         ("iso_guide_n", _i32), ("iso_guide_off", _i32), ("imf_n", _i32), ("imf_cdf_off", _i32),
-        ("imf_guide_n", _i32), ("imf_guide_off", _i32), ("cdf_guide_off", _i32), ("pad0_", _i32),
+        ("imf_guide_n", _i32), ("imf_guide_off", _i32), ("cdf_guide_off", _i32), ("iso_direct", _i32),
         ("imf_mass_lo", _f64), ("imf_mass_hi", _f64), ("imf_mass_step", _f64),
         ("iso_guide_x0", _f64), ("iso_guide_inv", _f64),
         ("R", _f64 * 9),
@@ -62,12 +62,13 @@ class SSParams(C.Structure):
         ("photo_error", SSFunc), ("completeness", SSFunc), ("detection", SSFunc),
         ("hist_enable", _i32), ("grid_lut_n", _i32),
         ("hist_lo", _f64 * N_HIST), ("hist_inv_width", _f64 * N_HIST),
-        ("math_mode", _i32), ("pad2_", _i32)]
+        ("math_mode", _i32), ("iso_lut_n", _i32)]
 
 
 class SSTables(C.Structure):
     _fields_ = [("blob", _vp), ("blob_bytes", _i64), ("cdf_pairs", _vp), ("cdf_perm", _vp),
-                ("grid", _vp), ("grid_rows", _vp), ("grid_lut", _vp), ("grid_thr", _vp)]
+                ("grid", _vp), ("grid_rows", _vp), ("grid_lut", _vp), ("grid_thr", _vp),
+                ("iso_rows", _vp), ("iso_lut", _vp), ("iso_thr", _vp)]
 
 
 class SSMaps(C.Structure):

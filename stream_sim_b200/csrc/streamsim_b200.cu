@@ -224,6 +224,48 @@ __device__ __forceinline__ double invcdf_phi1(const KArgs& a, const int32_t* __r
                         : __dadd_rn(__dmul_rn((double)idx, p.grid_step), p.density_lo);
 }
 
+// The isochrone magnitudes are a function of ONE uniform: mass = F_IMF^-1(u) is piecewise
+// linear in u on the 10000 IMF-CDF knots, mag_b(mass) piecewise linear on the isochrone
+// rows, so mag_b(u) is piecewise linear on the union of both sets of breakpoints.  The host
+// tabulates that composite (values at the breakpoints from the reference's own two-stage
+// arithmetic) and the device finds the segment with the same one-round-trip bucket table
+// as the phi1 grid: no search loops in shared memory, no division, 100 KB less shared
+// memory.  Rows: (U_k, g_k, dg/du, r_k, dr/du, 0); thr[k] = U_{k+1}.
+__device__ __forceinline__ void iso_sample_direct(const KArgs& a, double u, double& m1, double& m2,
+                                                  unsigned& domain_err) {
+  const SSParams& p = a.p;
+  if (!(u >= 0.0 && u <= 1.0)) {             // interp1d(bounds_error=True) raises
+    domain_err++;
+    m1 = m2 = ss::nan_d();
+    return;
+  }
+  long long idx;
+  if (u >= 1.0) {
+    idx = p.iso_n - 1;
+  } else {
+    const double fb = u * (double)p.iso_lut_n;
+    const int b = (int)fb;
+    const double2 e = __ldg(&reinterpret_cast<const double2*>(a.t.iso_lut)[b]);
+    const long long packed = __double_as_longlong(e.x);
+    const int lo = (int)(packed & 0xffffffffLL), k = (int)(packed >> 32);
+    if (k <= 1) {
+      idx = lo + ((k == 1 && u >= e.y) ? 1 : 0);
+    } else {
+      const double* __restrict__ thr = a.t.iso_thr;
+      int j = lo + (int)((fb - (double)b) * (double)k);
+      const int hi = lo + k;
+      while (j > lo && u < __ldg(&thr[j - 1])) --j;
+      while (j < hi && u >= __ldg(&thr[j])) ++j;
+      idx = j;
+    }
+  }
+  const double2* __restrict__ rows = reinterpret_cast<const double2*>(a.t.iso_rows);
+  const double2 r0 = __ldg(&rows[3 * idx]), r1 = __ldg(&rows[3 * idx + 1]), r2 = __ldg(&rows[3 * idx + 2]);
+  const double du = u - r0.x;
+  m1 = r0.y + r1.x * du;
+  m2 = r1.y + r2.x * du;
+}
+
 // ugali imf.sample + isochrone interp1d (reference model.py:590-602)
 __device__ __forceinline__ void iso_sample(const SSParams& p, const double* __restrict__ tab,
                                            const int32_t* __restrict__ itab, double u,
@@ -422,7 +464,8 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
         }
         if (has_iso) {
           double m1, m2;
-          iso_sample(p, tab, itab, u_mass, m1, m2, c_dom);
+          if (LEAN || p.iso_direct) iso_sample_direct(a, u_mass, m1, m2, c_dom);
+          else iso_sample(p, tab, itab, u_mass, m1, m2, c_dom);
           mag_g = __dadd_rn(m1, dist);
           mag_r = __dadd_rn(m2, dist);
         }
@@ -772,7 +815,7 @@ int launch_stage(uint32_t st, const KArgs& a, int smem, int grid, cudaStream_t s
     case 7: {
       const SSDraws& d = a.d;
       const bool lean = a.p.density_kind == SS_DENSITY_GRID && !a.p.nest && a.p.has_dist &&
-                        a.p.has_iso && a.p.band_present[0] && a.p.band_present[1] &&
+                        a.p.has_iso && a.p.iso_direct && a.p.band_present[0] && a.p.band_present[1] &&
                         !d.u_phi1 && !d.u_mass && !d.n_phi2 && !d.n_dist && !d.z_flux[0] &&
                         !d.z_flux[1] && !d.u_det && !d.u_det2 && !a.in.phi1 && !a.in.phi2 &&
                         !a.in.dist && !a.o.draws_out;
@@ -832,8 +875,14 @@ int validate(uint32_t st, const SSParams* p, const SSTables* t, const SSMaps* m,
     if (p->has_iso) {
       if (!p->has_dist && !(in && in->dist))
         return fail(SS_EINVAL, "isochrone magnitudes need a distance modulus%s");
-      if (p->iso_n < 2 || p->imf_n < 2) return fail(SS_EINVAL, "isochrone/IMF tables too short%s");
-      if (p->imf_guide_n & (p->imf_guide_n - 1)) return fail(SS_EINVAL, "imf_guide_n must be a power of two%s");
+      if (p->iso_direct) {
+        if (!t->iso_rows || !t->iso_lut || !t->iso_thr || p->iso_n < 2 || p->iso_lut_n < 1)
+          return fail(SS_EINVAL, "direct isochrone lookup needs iso_rows, iso_lut, iso_thr%s");
+      } else {
+        if (p->iso_n < 2 || p->imf_n < 2) return fail(SS_EINVAL, "isochrone/IMF tables too short%s");
+        if (p->imf_guide_n & (p->imf_guide_n - 1))
+          return fail(SS_EINVAL, "imf_guide_n must be a power of two%s");
+      }
     }
   }
   if ((st & SS_STAGE_ROTATE) && !(st & SS_STAGE_GENERATE)) {

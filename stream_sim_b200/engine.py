@@ -30,6 +30,7 @@ ROTATE_COLUMNS = ("ra", "dec")
 SNR_MIN = 5.0            # reference observed.py:267
 CDF_GUIDE = 8192
 IMF_GUIDE = 4096
+ISO_LUT = 1 << 15
 GRID_LUT = 1 << 17     # measured: 2^17 (2 MB, partly L1-resident) beats 2^15..2^20
 
 
@@ -224,7 +225,7 @@ class StarEngine:
     def __init__(self, stream=None, survey=None, frame=None, device=None, bands=("r", "g"),
                  nside=4096, dust_correction=True, perfect_galstarsep=False,
                  detection_mag_cut=("g",), nest=False, hist=None, cdf_steps=1e5,
-                 grid_table=True, math="f64"):
+                 grid_table=True, math="f64", iso_direct=True):
         torch = _torch()
         self.lib = _lib.load()
         self.device = require_device(device)
@@ -237,6 +238,7 @@ class StarEngine:
         packer = BlobPacker()
         p = self.params
         self._grid_table = bool(grid_table)
+        self._iso_direct = bool(iso_direct)
         if math not in ("f64", "mixed"):
             raise ValueError("math must be 'f64' or 'mixed'")
         self.params.math_mode = _lib.MATH_MIXED if math == "mixed" else _lib.MATH_F64
@@ -297,8 +299,39 @@ class StarEngine:
         iso = getattr(stream, "isochrone", None)
         if iso is not None:
             tab = iso.table
-            mg, mr = tab.mags_gr()
             p.has_iso = 1
+            if self._iso_direct:
+                self._set_iso_direct(tab)
+            else:
+                self._pack_iso_tables(tab, packer)
+
+    def _set_iso_direct(self, tab):
+        """Composite mags(u) table + bucket lookup (csrc ``iso_sample_direct``)."""
+        torch = _torch()
+        p = self.params
+        U, G, sg, R, sr = tab.composite()
+        n = len(U)
+        rows = np.zeros((n, 6))
+        rows[:, 0], rows[:, 1], rows[:, 2], rows[:, 3], rows[:, 4] = U, G, sg, R, sr
+        thr = np.concatenate([U[1:], [np.inf]])               # pass from row k to k+1
+        edges = np.searchsorted(thr[:-1], np.arange(ISO_LUT + 1) / ISO_LUT, side="right")
+        lo, k = edges[:-1].astype(np.int64), np.diff(edges).astype(np.int64)
+        lut = np.empty((ISO_LUT, 2))
+        lut[:, 0] = (lo | (k << 32)).view(np.float64)
+        lut[:, 1] = thr[lo]
+        self.iso_rows = torch.from_numpy(rows).to(self.device)
+        self.iso_lut = torch.from_numpy(lut).to(self.device)
+        self.iso_thr = torch.from_numpy(thr).to(self.device)
+        self.tables.iso_rows = self.iso_rows.data_ptr()
+        self.tables.iso_lut = self.iso_lut.data_ptr()
+        self.tables.iso_thr = self.iso_thr.data_ptr()
+        p.iso_direct, p.iso_n, p.iso_lut_n = 1, n, ISO_LUT
+
+    def _pack_iso_tables(self, tab, packer):
+        """Two-stage tables in the shared-memory blob (csrc ``iso_sample``)."""
+        p = self.params
+        if True:
+            mg, mr = tab.mags_gr()
             p.iso_n = len(tab.mass_init)
             with np.errstate(divide="ignore", invalid="ignore"):
                 dm = tab.mass_init[1:] - tab.mass_init[:-1]
@@ -383,7 +416,8 @@ class StarEngine:
 
     def model_tensors(self):
         """Device tensors that make up the model/survey tables (not the maps)."""
-        names = ("blob", "cdf_pairs", "cdf_perm", "grid", "grid_rows", "grid_lut", "grid_thr")
+        names = ("blob", "cdf_pairs", "cdf_perm", "grid", "grid_rows", "grid_lut", "grid_thr",
+                 "iso_rows", "iso_lut", "iso_thr")
         return [getattr(self, k) for k in names if getattr(self, k, None) is not None]
 
     # ---- rotate

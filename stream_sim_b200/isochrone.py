@@ -68,6 +68,29 @@ class IsochroneTable:
             return self.mag_2, self.mag_1
         return self.mag_1, self.mag_2
 
+    def composite(self):
+        """mag_g(u), mag_r(u) as ONE piecewise-linear table over the uniform draw u.
+
+        mass(u) (ugali's IMF inverse transform) is piecewise linear on the CDF knots and
+        mag(mass) piecewise linear on the isochrone rows, so their composition is
+        piecewise linear on the union of the CDF knots and of the u values at which the
+        mass crosses an isochrone row.  Breakpoint values come from the two-stage
+        arithmetic itself.  Returns (U, mag_g, dmag_g/du, mag_r, dmag_r/du), the slopes
+        being 0 on the last row."""
+        mg, mr = self.mags_gr()
+        inner = self.mass_init[(self.mass_init > self.mass_grid[0])
+                               & (self.mass_init < self.mass_grid[-1])]
+        u_knots = np.interp(inner, self.mass_grid, self.cdf)
+        U = np.unique(np.concatenate([self.cdf, u_knots]))
+        U = U[(U >= 0.0) & (U <= 1.0)]
+        mass = np.interp(U, self.cdf, self.mass_grid)
+        G = np.interp(mass, self.mass_init, mg)
+        R = np.interp(mass, self.mass_init, mr)
+        dU = np.diff(U)
+        sg = np.concatenate([np.diff(G) / dU, [0.0]])
+        sr = np.concatenate([np.diff(R) / dU, [0.0]])
+        return U, G, sg, R, sr
+
     @classmethod
     def synthetic(cls, n=256):
         from .synthetic import isochrone_table
