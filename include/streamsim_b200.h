@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SS_ABI_VERSION 9
+#define SS_ABI_VERSION 10
 
 /* error codes */
 #define SS_OK 0
@@ -199,6 +199,10 @@ typedef struct SSParams {
 typedef struct SSTables {
   const void* blob;          /* packed small tables (doubles; int32 guides embedded)    */
   int64_t blob_bytes;        /* multiple of 16                                    */
+  int64_t blob_hot_bytes;    /* leading part staged into shared memory (0 = all); the
+                                stream-model tables may lie beyond it when a phi1 grid
+                                table is present (they are then read from global memory,
+                                and only on the generic path)                       */
   const double* cdf_pairs;   /* [cdf_n][2] = (sorted cdf_j, slope_j)              */
   const int32_t* cdf_perm;   /* [cdf_n] original index of sorted entry j; NULL if identity */
   const double* grid;        /* [cdf_n] explicit phi1 grid, or NULL = start + j*step */

@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 # ---- constants mirrored from the header
 STAGE_GENERATE, STAGE_ROTATE, STAGE_OBSERVE = 1, 2, 4
@@ -66,7 +66,7 @@ class SSParams(C.Structure):
 
 
 class SSTables(C.Structure):
-    _fields_ = [("blob", _vp), ("blob_bytes", _i64), ("cdf_pairs", _vp), ("cdf_perm", _vp),
+    _fields_ = [("blob", _vp), ("blob_bytes", _i64), ("blob_hot_bytes", _i64), ("cdf_pairs", _vp), ("cdf_perm", _vp),
                 ("grid", _vp), ("grid_rows", _vp), ("grid_lut", _vp), ("grid_thr", _vp),
                 ("iso_rows", _vp), ("iso_lut", _vp), ("iso_thr", _vp)]
 

@@ -366,6 +366,10 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
   if (want_hist)
     for (int i = threadIdx.x; i < SS_N_HIST * SS_HIST_BINS; i += blockDim.x) s_hist[i] = 0;
 
+  // `tab`: the hot part of the blob (first blob_hot_bytes), staged into shared memory.
+  // `stab`: base for the stream-model tables (track / distance-modulus knots, inverse-CDF
+  // guide) -- the same shared copy, or, when the phi1 grid table makes them cold, the
+  // global blob (shared memory not spent on them is L1 cache for the gathers).
   const double* tab;
   if (a.blob_in_smem) {
     stage_blob(smem_blob, a.t.blob, a.blob_bytes, &s_bar);
@@ -373,7 +377,10 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
   } else {
     tab = reinterpret_cast<const double*>(a.t.blob);
   }
+  const double* stab = (a.t.blob_hot_bytes < a.t.blob_bytes)
+                           ? reinterpret_cast<const double*>(a.t.blob) : tab;
   const int32_t* itab = reinterpret_cast<const int32_t*>(tab);
+  const int32_t* sitab = reinterpret_cast<const int32_t*>(stab);
   __syncthreads();
 
   unsigned c_obs = 0, c_perf = 0, c_bad_g = 0, c_bad_r = 0, c_unseen = 0, c_dom = 0, c_coord = 0,
@@ -412,7 +419,7 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
       } else if (density_kind == SS_DENSITY_UNIFORM) {
         phi1 = __dadd_rn(__dmul_rn(u_phi1, __dsub_rn(p.density_hi, p.density_lo)), p.density_lo);
       } else if (density_kind == SS_DENSITY_INVCDF) {
-        phi1 = invcdf_phi1(a, itab, u_phi1);
+        phi1 = invcdf_phi1(a, sitab, u_phi1);
       } else if (density_kind == SS_DENSITY_GAUSSIAN) {  // u_phi1 slot carries a normal draw
         double z = u_phi1;
         if (!d_u_phi1) {
@@ -451,7 +458,7 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
         phi2 = phi2_given;
       } else {
         double c = row.c, s = row.s;
-        if (!LEAN && !on_grid) track_eval(p.track_center, p.track_spread, tab, phi1, c, s);
+        if (!LEAN && !on_grid) track_eval(p.track_center, p.track_spread, stab, phi1, c, s);
         phi2 = track_draw(c, s, p.track_sampler, n_phi2, c_dom);
       }
       const double dist_given = in_dist ? in_dist[i] : ss::nan_d();
@@ -459,7 +466,7 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
       if (has_dist || has_iso) {
         if (!(dist_given == dist_given) && has_dist) {
           double c = row.dc, s = row.ds;
-          if (!LEAN && !on_grid) track_eval(p.dist_center, p.dist_spread, tab, phi1, c, s);
+          if (!LEAN && !on_grid) track_eval(p.dist_center, p.dist_spread, stab, phi1, c, s);
           dist = track_draw(c, s, p.dist_sampler, n_dist, c_dom);
         }
         if (has_iso) {
@@ -852,6 +859,8 @@ int validate(uint32_t st, const SSParams* p, const SSTables* t, const SSMaps* m,
     return fail(SS_EINVAL, "SS_MATH_MIXED is available for the observe and fused stage masks%s");
   const int64_t nd = t ? t->blob_bytes / 8 : 0;
   if (t && (t->blob_bytes % 16 != 0)) return fail(SS_EINVAL, "blob_bytes must be a multiple of 16%s");
+  if (t && (t->blob_hot_bytes % 16 != 0 || t->blob_hot_bytes < 0 || t->blob_hot_bytes > t->blob_bytes))
+    return fail(SS_EINVAL, "blob_hot_bytes must be a multiple of 16 within the blob%s");
   if (st & SS_STAGE_GENERATE) {
     if (!t) return fail(SS_EINVAL, "generate needs tables%s");
     int rc;
@@ -971,9 +980,12 @@ int ss_run(uint32_t stages, const SSParams* p, const SSTables* t, const SSMaps* 
   a.offset = star_offset;
   a.seed = seed;
   int smem, grid;
-  plan_launch(dev, a.t.blob_bytes, n, smem, grid);
+  if (a.t.blob_hot_bytes <= 0 || a.t.blob_hot_bytes > a.t.blob_bytes)
+    a.t.blob_hot_bytes = a.t.blob_bytes;
+  plan_launch(dev, a.t.blob_hot_bytes, n, smem, grid);
   a.blob_in_smem = smem > 0;
-  a.blob_bytes = (uint32_t)a.t.blob_bytes;
+  a.blob_bytes = (uint32_t)a.t.blob_hot_bytes;                 // what stage_blob copies
+  if (!a.blob_in_smem) a.t.blob_hot_bytes = a.t.blob_bytes;   // everything read from global
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   return out->dtype == SS_DTYPE_F32 ? launch_stage<float>(stages, a, smem, grid, s)
                                     : launch_stage<double>(stages, a, smem, grid, s);

@@ -135,6 +135,18 @@ class BlobPacker:
         return d.view(np.uint8)
 
 
+def _rebase(f, base):
+    """Shift the blob offsets of an SSFunc packed into the cold region."""
+    if f.kind in (_lib.FN_LINEAR, _lib.FN_SPLINE, _lib.FN_SPLINE_PRODUCT):
+        f.x_off += base
+        f.c_off += base
+        if f.g_n > 0:
+            f.g_off += base
+        if f.kind == _lib.FN_SPLINE_PRODUCT:
+            f.x2_off += base
+            f.c2_off += base
+
+
 def search_guide(sorted_vals, guide_n):
     """guide[g] = last index j with sorted_vals[j] <= g/guide_n (0 if none)."""
     edges = np.arange(guide_n + 1, dtype=float) / guide_n
@@ -235,27 +247,40 @@ class StarEngine:
         self.has_generate = stream is not None
         self.has_observe = survey is not None
         self._keep = []                    # tensors referenced by raw pointers
-        packer = BlobPacker()
+        # two regions of the table blob: `hot` is staged into shared memory by every CTA;
+        # `cold` holds the stream-model tables (track / distance-modulus knots, inverse-CDF
+        # guide), which the kernel only touches on the generic path once a phi1 grid table
+        # exists -- shared memory not spent on them is L1 cache for the gathers
+        hot, cold = BlobPacker(), BlobPacker()
         p = self.params
         self._grid_table = bool(grid_table)
         self._iso_direct = bool(iso_direct)
         if math not in ("f64", "mixed"):
             raise ValueError("math must be 'f64' or 'mixed'")
         self.params.math_mode = _lib.MATH_MIXED if math == "mixed" else _lib.MATH_F64
-        if stream is not None:
-            self._describe_stream(stream, packer, int(cdf_steps))
-        self.set_frame(frame)
         if survey is not None:
-            self._describe_survey(survey, packer, bands, nside, dust_correction,
+            self._describe_survey(survey, hot, bands, nside, dust_correction,
                                   perfect_galstarsep, detection_mag_cut, nest)
+        if stream is not None:
+            self._describe_stream(stream, hot, cold, int(cdf_steps))
+        self.set_frame(frame)
         self._describe_hist(hist)
-        blob = packer.finalize()
+        hot_blob, cold_blob = hot.finalize(), cold.finalize()
+        base = hot_blob.size // 8
+        for f in (p.track_center, p.track_spread, p.dist_center, p.dist_spread):
+            _rebase(f, base)
+        p.cdf_guide_off += base
+        blob = np.concatenate([hot_blob, cold_blob])
         self.blob = torch.from_numpy(blob).to(self.device)
         self.tables.blob = self.blob.data_ptr()
+        self.tables.blob_hot_bytes = (hot_blob.size if p.density_kind == _lib.DENSITY_GRID
+                                      else blob.size)
         self.tables.blob_bytes = self.blob.numel()
 
     # ---- generate-side description (reference model.py:57-104, samplers.py)
-    def _describe_stream(self, stream, packer, cdf_steps):
+    def _describe_stream(self, stream, hot, packer, cdf_steps):
+        """``packer`` (the cold region) receives the density guide and the track /
+        distance-modulus tables, ``hot`` the two-stage isochrone tables."""
         from . import samplers as S
         torch = _torch()
         p = self.params
@@ -303,7 +328,7 @@ class StarEngine:
             if self._iso_direct:
                 self._set_iso_direct(tab)
             else:
-                self._pack_iso_tables(tab, packer)
+                self._pack_iso_tables(tab, hot)
 
     def _set_iso_direct(self, tab):
         """Composite mags(u) table + bucket lookup (csrc ``iso_sample_direct``)."""
