@@ -371,8 +371,8 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
   // guide) -- the same shared copy, or, when the phi1 grid table makes them cold, the
   // global blob (shared memory not spent on them is L1 cache for the gathers).
   const double* tab;
-  if (a.blob_in_smem) {
-    stage_blob(smem_blob, a.t.blob, a.blob_bytes, &s_bar);
+  if (LEAN || a.blob_in_smem) {   // LEAN is only launched with the hot tables in shared memory:
+    stage_blob(smem_blob, a.t.blob, a.blob_bytes, &s_bar);   // its table reads compile to LDS
     tab = reinterpret_cast<const double*>(smem_blob);
   } else {
     tab = reinterpret_cast<const double*>(a.t.blob);
@@ -827,10 +827,10 @@ int launch_stage(uint32_t st, const KArgs& a, int smem, int grid, cudaStream_t s
                         !d.z_flux[1] && !d.u_det && !d.u_det2 && !a.in.phi1 && !a.in.phi2 &&
                         !a.in.dist && !a.o.draws_out;
       if (a.p.math_mode == SS_MATH_MIXED)
-        return lean ? launch_t<7, OutT, true, SS_MATH_MIXED>(a, smem, grid, s)
-                    : launch_t<7, OutT, false, SS_MATH_MIXED>(a, smem, grid, s);
-      return lean ? launch_t<7, OutT, true>(a, smem, grid, s)
-                  : launch_t<7, OutT, false>(a, smem, grid, s);
+        return (lean && smem > 0) ? launch_t<7, OutT, true, SS_MATH_MIXED>(a, smem, grid, s)
+                                  : launch_t<7, OutT, false, SS_MATH_MIXED>(a, smem, grid, s);
+      return (lean && smem > 0) ? launch_t<7, OutT, true>(a, smem, grid, s)
+                                : launch_t<7, OutT, false>(a, smem, grid, s);
     }
   }
   return fail(SS_EINVAL, "unsupported stage mask%s");
