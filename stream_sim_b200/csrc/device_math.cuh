@@ -58,17 +58,170 @@ __device__ __forceinline__ void bm32(uint32_t wa, uint32_t wb, double& z0, doubl
   z1 = (double)(r * s);
 }
 
+// ---------------------------------------------------------------- elementary functions
+// Own double-precision log10 / 10^x / atan2 / small-angle sincos for the hot loop.  The
+// CUDA library versions are accurate but spell every polynomial coefficient as two
+// 32-bit immediates (two UMOV per DFMA: 12 % of the kernel's issued instructions in the
+// round-1 ncu captures); here the coefficients sit in the constant bank and arrive two
+// per LDCU.128.  All are good to <= 2 ulp on their stated domains (tests/test_gpu_math.py
+// checks them against NumPy through ss_math_probe).
+__constant__ __align__(16) double kSinC[8] = {
+    1.0, -1.0 / 6, 1.0 / 120, -1.0 / 5040, 1.0 / 362880, -1.0 / 39916800, 1.0 / 6227020800.0,
+    -1.0 / 1307674368000.0};
+__constant__ __align__(16) double kCosC[8] = {
+    -0.5, 1.0 / 24, -1.0 / 720, 1.0 / 40320, -1.0 / 3628800, 1.0 / 479001600,
+    -1.0 / 87178291200.0, 1.0 / 20922789888000.0};
+// (2/ln 10)/(2k+1), k = 0..10: log10(m) = s * sum_k kLogC[k] s^(2k), s = (m-1)/(m+1)
+__constant__ __align__(16) double kLogC[12] = {
+    0.8685889638065036, 0.2895296546021679, 0.17371779276130073, 0.12408413768664338,
+    0.09650988486738929, 0.07896263307331851, 0.06681453567742336, 0.05790593092043358,
+    0.0510934684592061, 0.04571520862139493, 0.041361379228881126, 0.0};
+// (ln 2)^k / k!, k = 1..14
+__constant__ __align__(16) double kExp2C[14] = {
+    0.6931471805599453, 0.24022650695910072, 0.05550410866482158, 0.009618129107628477,
+    0.0013333558146428443, 0.0001540353039338161, 1.5252733804059841e-05,
+    1.321548679014431e-06, 1.01780860092397e-07, 7.054911620801123e-09,
+    4.4455382718708116e-10, 2.5678435993488206e-11, 1.3691488853904128e-12,
+    6.778726354822545e-14};
+// (-1)^k/(2k+1), k = 1..7: atan(r) = r + r^3 * (...)
+__constant__ __align__(16) double kAtanC[8] = {
+    -1.0 / 3, 1.0 / 5, -1.0 / 7, 1.0 / 9, -1.0 / 11, 1.0 / 13, -1.0 / 15, 0.0};
+// atan(i/8) as (hi, lo), i = 0..8
+__constant__ __align__(16) double kAtanT[32] = {
+    0.0, 0.0,
+    0.12435499454676144, -3.1253241424539383e-18,
+    0.24497866312686414, 1.0698755618734451e-17,
+    0.35877067027057225, -2.4623815582638635e-17,
+    0.4636476090008061, 2.2698777452961687e-17,
+    0.5585993153435624, -5.4556305485916264e-18,
+    0.6435011087932844, 1.5834785051444286e-17,
+    0.7188299996216245, -2.1478388444456983e-17,
+    0.7853981633974483, 3.061616997868383e-17};
+// scalars: [0] log2(10) hi, [1] lo, [2] log10(2), [3] pi/2 hi, [4] lo, [5] pi hi, [6] lo,
+// [7] 180/pi, [8] pi/180, [9] 2/pi, [10] 1.5*2^52, [11] 1/1.0857362
+__constant__ __align__(16) double kNum[12] = {
+    3.321928094887362, 1.661617516973592e-16, 0.3010299956639812, 1.5707963267948966,
+    6.123233995736766e-17, 3.141592653589793, 1.2246467991473532e-16, 57.29577951308232,
+    0.017453292519943295, 0.6366197723675814, 6755399441055744.0, 1.0 / 1.0857362};
+
+// The *_nb functions are branch-free (no fallback, no slow path) so that several of them
+// placed in one basic block interleave their dependency chains: the kernel is bound by
+// the latency of dependent double-precision instructions at 8 warps per scheduler, not
+// by instruction count.  Their domains are the callers' responsibility.
+
+// 1/d for a normal positive double: MUFU.RCP64H seed (20 bits) + one Newton step (40 bits);
+// div_pos finishes with a residual correction of the quotient
+__device__ __forceinline__ double rcp40_pos(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  return fma(fma(-d, r, 1.0), r, r);
+}
+
+// a/d, d normal positive (<= 1 ulp)
+__device__ __forceinline__ double div_pos(double a, double d) {
+  const double r = rcp40_pos(d);
+  const double q = a * r;
+  return fma(fma(-q, d, a), r, q);
+}
+
+// sqrt(a), a normal positive or 0 (NaN propagates); correctly rounded up to rare ties
+__device__ __forceinline__ double sqrt_nb(double a) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double g = a * y, h = 0.5 * y;
+  double r = fma(-h, g, 0.5);
+  g = fma(g, r, g);
+  h = fma(h, r, h);
+  r = fma(-h, g, 0.5);
+  g = fma(g, r, g);
+  h = fma(h, r, h);
+  g = fma(fma(-g, g, a), h, g);
+  return (a == 0.0) ? 0.0 : g;
+}
+
+// log10(t) for normal t > 0 (anything else: garbage, the caller selects)
+__device__ __forceinline__ double log10_nb(double t) {
+  int hi = __double2hiint(t);
+  int e = (hi >> 20) - 1023;
+  hi = (hi & 0x000fffff) | 0x3ff00000;
+  const bool up = hi >= 0x3ff6a09f;                        // m in [sqrt(1/2), sqrt 2)
+  hi -= up ? 0x00100000 : 0;
+  e += up ? 1 : 0;
+  const double m = __hiloint2double(hi, __double2loint(t));
+  const double s = div_pos(m - 1.0, m + 1.0);
+  const double s2 = s * s, s4 = s2 * s2;
+  // sum_{k=1..10} kLogC[k] s2^(k-1), even / odd halves evaluated side by side
+  double pe = kLogC[9], po = kLogC[10];
+  pe = fma(pe, s4, kLogC[7]); po = fma(po, s4, kLogC[8]);
+  pe = fma(pe, s4, kLogC[5]); po = fma(po, s4, kLogC[6]);
+  pe = fma(pe, s4, kLogC[3]); po = fma(po, s4, kLogC[4]);
+  pe = fma(pe, s4, kLogC[1]); po = fma(po, s4, kLogC[2]);
+  const double p = fma(po, s2, pe);
+  const double lm = fma(s * s2, p, s * kLogC[0]);          // log10(m)
+  return fma((double)e, kNum[2], lm);
+}
+
+// 10^x for |x| < 300 (NaN propagates)
+__device__ __forceinline__ double exp10_nb(double x) {
+  const double t = fma(x, kNum[0], kNum[10]);               // round(x log2 10) in the low word
+  const int n = __double2loint(t);
+  const double nd = t - kNum[10];
+  const double f = fma(x, kNum[1], fma(x, kNum[0], -nd));   // |f| <= 1/2
+  const double f2 = f * f;
+  // 2^f = 1 + f * sum_{k=0..13} kExp2C[k] f^k, even / odd halves side by side
+  double pe = kExp2C[12], po = kExp2C[13];
+#pragma unroll
+  for (int k = 10; k >= 0; k -= 2) {
+    pe = fma(pe, f2, kExp2C[k]);
+    po = fma(po, f2, kExp2C[k + 1]);
+  }
+  const double p = fma(fma(po, f, pe), f, 1.0);
+  return p * __hiloint2double((n + 1023) << 20, 0);
+}
+
+__device__ __forceinline__ double exp10_fast(double x) {
+  return (fabs(x) < 300.0 || x != x) ? exp10_nb(x) : exp10(x);
+}
+
+// atan2(y, x) for finite arguments whose larger magnitude is a normal number (0 for
+// x = y = 0).  q = min/max in [0,1] is reduced against the nearest i/8:
+// atan(q) = atan(i/8) + atan((q - c)/(1 + q c)), |r| <= 1/16, one division.
+__device__ __forceinline__ double atan2_nb(double y, double x) {
+  const double ax = fabs(x), ay = fabs(y);
+  const double mx = fmax(ax, ay), mn = fmin(ax, ay);
+  double r0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(mx));
+  const double t = fma(mn * r0, 8.0, kNum[10]);
+  const int i = __double2loint(t) & 15;                     // 0..8
+  const double c = (t - kNum[10]) * 0.125;
+  const double r = div_pos(fma(-c, mx, mn), fma(c, mn, mx));
+  const double r2 = r * r, r4 = r2 * r2;
+  // atan(r) = r + r^3 sum_k kAtanC[k] r2^k (k = 0..6), even / odd halves side by side
+  double pe = fma(kAtanC[6], r4, kAtanC[4]), po = kAtanC[5];
+  pe = fma(pe, r4, kAtanC[2]); po = fma(po, r4, kAtanC[3]);
+  pe = fma(pe, r4, kAtanC[0]); po = fma(po, r4, kAtanC[1]);
+  const double p = fma(po, r2, pe);
+  double a = kAtanT[2 * i] + (fma(r * r2, p, r) + kAtanT[2 * i + 1]);
+  a = (ay > ax) ? (kNum[3] - a) + kNum[4] : a;
+  a = (x < 0.0) ? (kNum[5] - a) + kNum[6] : a;
+  a = (mx == 0.0) ? 0.0 : a;
+  return (y < 0.0) ? -a : a;
+}
+
 // sin and cos of a small angle (|b| <= 0.26 rad ~ 15 deg: the transverse stream
-// coordinate) by Taylor series to full double precision -- ~20 FMAs instead of a
-// general-range sincos; larger angles take the library path.
+// coordinate) by Taylor series to full double precision; larger angles take the
+// library path.
 __device__ __forceinline__ void sincos_small(double b, double& s, double& c) {
   if (fabs(b) <= 0.26) {
     const double x = b * b;
-    s = b * (1.0 + x * (-1.0 / 6 + x * (1.0 / 120 + x * (-1.0 / 5040 + x * (1.0 / 362880 +
-        x * (-1.0 / 39916800 + x * (1.0 / 6227020800.0 + x * (-1.0 / 1307674368000.0))))))));
-    c = 1.0 + x * (-0.5 + x * (1.0 / 24 + x * (-1.0 / 720 + x * (1.0 / 40320 +
-        x * (-1.0 / 3628800 + x * (1.0 / 479001600 + x * (-1.0 / 87178291200.0 +
-        x * (1.0 / 20922789888000.0))))))));
+    double ps = kSinC[7], pc = kCosC[7];
+#pragma unroll
+    for (int k = 6; k >= 0; --k) {
+      ps = fma(ps, x, kSinC[k]);
+      pc = fma(pc, x, kCosC[k]);
+    }
+    s = b * ps;
+    c = fma(pc, x, 1.0);
   } else {
     sincos(b, &s, &c);
   }
@@ -304,7 +457,7 @@ __device__ __forceinline__ double photo_error_log(const SSParams& p, const doubl
 // statistical (+) systematic error in quadrature (reference surveys.py:288-290)
 __device__ __forceinline__ double photo_error_total(const SSParams& p, int band, double loge,
                                                     bool bright) {
-  const double stat = bright ? p.err_bright : exp10(loge);
+  const double stat = bright ? p.err_bright : exp10_fast(loge);
   const double sys = p.sys_error[band];
   return sqrt(__dadd_rn(__dmul_rn(stat, stat), __dmul_rn(sys, sys)));
 }

@@ -492,17 +492,18 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
       }
       double sl = row.sinx, cl = row.cosx, sb, cb;
       if (!LEAN && !on_grid) sincospi(phi1 * (1.0 / 180.0), &sl, &cl);
-      ss::sincos_small(phi2 * 0.017453292519943295, sb, cb);
+      ss::sincos_small(phi2 * ss::kNum[8], sb, cb);
       const double v0 = cb * cl, v1 = cb * sl, v2 = sb;
       wx = p.R[0] * v0 + p.R[3] * v1 + p.R[6] * v2;
       wy = p.R[1] * v0 + p.R[4] * v1 + p.R[7] * v2;
       wz = p.R[2] * v0 + p.R[5] * v1 + p.R[8] * v2;
-      const double R2D = 57.29577951308232;
-      lon = atan2(wy, wx);
+      const double R2D = ss::kNum[7];
+      // astropy: lon = atan2(y, x), lat = atan2(z, hypot(x, y)).  |w| = 1, so the branch-
+      // free versions are inside their domains; the two chains interleave.
+      lon = ss::atan2_nb(wy, wx);
+      dec = ss::atan2_nb(wz, ss::sqrt_nb(wx * wx + wy * wy)) * R2D;
       ra = lon * R2D;
-      if (ra < 0.0) ra += 360.0;
-      // |w| = 1 to rounding: asin(w_z) is astropy's atan2(w_z, hypot(w_x, w_y)) to 1 ulp
-      dec = (fabs(wz) <= 1.0 ? asin(wz) : atan2(wz, sqrt(wx * wx + wy * wy))) * R2D;
+      ra = (ra < 0.0) ? ra + 360.0 : ra;
       put<OutT>(a.o.ra, i, ra);
       put<OutT>(a.o.dec, i, dec);
     }
@@ -523,7 +524,7 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
         // the rotated unit vector (the reference goes through degrees and back; equal to
         // ~1e-16).  Within 0.8 deg of a pole the reference's own chain is used.
         L.z = wz;
-        const double v = __dmul_rn(lon, 0.6366197723675813430755350534900574);
+        const double v = __dmul_rn(lon, ss::kNum[9]);
         L.tt = (v < 0.0) ? v + 4.0 : v;
         if (L.tt >= 4.0) L.tt = 0.0;
         L.sth = 0.0;
@@ -587,6 +588,82 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
         draws_out[SS_DRAW_U_DET2 * a.n + i] = u_det2;
       }
       bool valid = true, flag_c = false, flag_d = false, snr_ok = true, snr_r_ok = true;
+      if (MATH == SS_MATH_F64) {
+        // Stage 1: per band, the table look-ups (short, branchy).  Stage 2: the error /
+        // noise arithmetic of BOTH bands as one straight-line block of branch-free
+        // double-precision code, so that the two long dependency chains
+        // (10^x -> sqrt -> log10) interleave instead of running back to back.
+        double ext2[2], mt2[2], loge2[2], zf2[2], err2[2], mobs2[2];
+        bool bright2[2], have2[2], good2[2];
+        bool plain = true;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          have2[b] = (b == SS_BAND_G) ? band_g : band_r;
+          const double mag = b == SS_BAND_G ? mag_g : mag_r;
+          const double maglim = b == SS_BAND_G ? ml_g : ml_r;
+          zf2[b] = b == SS_BAND_G ? z_g : z_r;
+          ext2[b] = __dmul_rn(p.coeff_extinc[b], ebv);                   // surveys.py:228
+          mt2[b] = __dadd_rn(mag, ext2[b]);                              // observed.py:167
+          bright2[b] = false;
+          loge2[b] = ss::nan_d();
+          if (!have2[b]) continue;
+          loge2[b] = ss::photo_error_log(p, tab, b, mt2[b], maglim, bright2[b]);  // surveys.py:234-286
+          plain = plain && fabs(mt2[b]) < 200.0 && !(fabs(loge2[b]) >= 300.0);
+          if (b == p.completeness_band) {                                // observed.py:224-243
+            flag_c = u_det <= ss::efficiency(p, p.completeness, tab, b, mt2[b], maglim);
+            if (p.perfect_galstarsep)
+              flag_d = u_det2 <= ss::efficiency(p, p.detection, tab, b, mt2[b], maglim);
+            if (maglim != maglim) c_unseen++;
+          }
+        }
+        if (plain) {
+          // sample_measured_magnitudes (observed.py:863-904, :984-1035):
+          //   F = 3631*10^(-0.4 m), F_obs = F + (F*err/1.0857362)*z, m_obs = -2.5 log10(F_obs/3631)
+          // For magnitudes whose flux neither under- nor overflows this is, to rounding,
+          //   F_obs > 0  <=>  t > 0,   m_obs = m - 2.5 log10(t),   t = 1 + (err/1.0857362)*z
+          // which needs one log10 instead of exp10 + log10 + two divisions.
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            const double stat = bright2[b] ? p.err_bright : ss::exp10_nb(loge2[b]);
+            const double sys = p.sys_error[b];                           // surveys.py:288-290
+            err2[b] = ss::sqrt_nb(__dadd_rn(__dmul_rn(stat, stat), __dmul_rn(sys, sys)));
+            const double t = 1.0 + err2[b] * ss::kNum[11] * zf2[b];
+            good2[b] = t > 0.0;
+            mobs2[b] = good2[b] ? mt2[b] - 2.5 * ss::log10_nb(t) : ss::nan_d();
+          }
+        } else {
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            if (!have2[b]) continue;
+            err2[b] = ss::photo_error_total(p, b, loge2[b], bright2[b]);
+            mobs2[b] = ss::nan_d();
+            if (fabs(mt2[b]) < 200.0) {
+              const double t = 1.0 + err2[b] * ss::kNum[11] * zf2[b];
+              good2[b] = t > 0.0;
+              if (good2[b]) mobs2[b] = mt2[b] - 2.5 * log10(t);
+            } else {
+              const double flux = __dmul_rn(3631.0, exp10(__dmul_rn(-0.4, mt2[b])));
+              const double sig = __ddiv_rn(__dmul_rn(flux, err2[b]), 1.0857362);
+              const double fobs = __dadd_rn(flux, __dmul_rn(sig, zf2[b]));
+              good2[b] = fobs > 0.0;
+              if (good2[b]) mobs2[b] = __dmul_rn(-2.5, log10(__ddiv_rn(fobs, 3631.0)));
+            }
+          }
+        }
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          if (!have2[b]) continue;
+          const bool good = good2[b];
+          double mobs = mobs2[b];
+          if (good && p.dust_correction) mobs = __dsub_rn(mobs, ext2[b]);  // observed.py:194-208
+          valid = valid && good;
+          if (!good) { if (b == SS_BAND_G) c_bad_g++; else c_bad_r++; }
+          if (p.snr_cut[b]) snr_ok = snr_ok && (err2[b] <= p.snr_err_max);   // observed.py:266-281
+          if (b == SS_BAND_R) snr_r_ok = (err2[b] <= p.snr_err_max);         // observed.py:283-286
+          put<OutT>(a.o.mag_obs[b], i, mobs);
+          put<OutT>(a.o.magerr[b], i, err2[b]);
+        }
+      } else {
 #pragma unroll
       for (int b = 0; b < 2; ++b) {
         if (!(b == SS_BAND_G ? band_g : band_r)) continue;
@@ -636,7 +713,7 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
         if (!done) {
           err = ss::photo_error_total(p, b, loge, bright);                 // surveys.py:288-290
           if (fabs(m_true) < 200.0) {
-            const double t = 1.0 + err * (1.0 / 1.0857362) * zf;
+            const double t = 1.0 + err * ss::kNum[11] * zf;
             good = t > 0.0;
             if (good) mobs = m_true - 2.5 * log10(t);
           } else {
@@ -660,6 +737,7 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
         }
         put<OutT>(a.o.mag_obs[b], i, mobs);
         put<OutT>(a.o.magerr[b], i, err);
+      }
       }
       const bool observed = valid && flag_c && snr_ok;
       const bool perfect = p.perfect_galstarsep && valid && flag_d && snr_ok && snr_r_ok;
