@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SS_ABI_VERSION 10
+#define SS_ABI_VERSION 11
 
 /* error codes */
 #define SS_OK 0
@@ -306,6 +306,18 @@ int ss_eval_function(const SSFunc* f, const SSTables* t, const double* x, double
                      uint64_t n, void* stream);
 int ss_ang2pix(int32_t nside, int32_t nest, const double* lon_deg, const double* lat_deg,
                int64_t* pix, uint64_t n, void* stream);
+
+/* The kernel's own double-precision elementary functions, element-wise on device arrays,
+ * so that tests can hold them against libm/NumPy: fn = SS_MATH_FN_LOG10 (x > 0),
+ * _EXP10 (|x| < 300), _ATAN2 (y = x[], x = y2[]), _SQRT (x >= 0).  `y2` is only read by
+ * _ATAN2.  Replaces nothing in the reference (NumPy ufuncs np.log10, 10**x, np.arctan2,
+ * np.sqrt at observed.py:984-1035, surveys.py:288-290 and astropy's lon/lat). */
+#define SS_MATH_FN_LOG10 0
+#define SS_MATH_FN_EXP10 1
+#define SS_MATH_FN_ATAN2 2
+#define SS_MATH_FN_SQRT 3
+int ss_math_probe(int32_t fn, const double* x, const double* y2, double* out, uint64_t n,
+                  void* stream);
 
 /* Host-buffer variant of ss_generate_observe: every SSOut column pointer (and
  * counters) is a HOST pointer (pinned for full speed).  Stars are produced in

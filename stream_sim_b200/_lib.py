@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 # ---- constants mirrored from the header
 STAGE_GENERATE, STAGE_ROTATE, STAGE_OBSERVE = 1, 2, 4
@@ -115,6 +115,7 @@ SYMBOLS = {
     "ss_efficiency": (C.c_int, [_P(SSParams), _P(SSTables), _i32, _i32, _vp, _vp, _vp, _u64, _vp]),
     "ss_eval_function": (C.c_int, [_P(SSFunc), _P(SSTables), _vp, _vp, _u64, _vp]),
     "ss_ang2pix": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _u64, _vp]),
+    "ss_math_probe": (C.c_int, [_i32, _vp, _vp, _vp, _u64, _vp]),
     "ss_host_workspace_bytes": (_i64, [_u64, _i32]),
     "ss_generate_observe_host": (C.c_int, [_P(SSParams), _P(SSTables), _P(SSMaps), _P(SSOut),
                                            _u64, _u64, _u64, _vp, _i64, _u64]),

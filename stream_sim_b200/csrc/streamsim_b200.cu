@@ -834,6 +834,23 @@ __global__ void k_ang2pix(int nside, int nest, const double* lon, const double* 
   }
 }
 
+__global__ void k_math_probe(int fn, const double* x, const double* y2, double* out,
+                             unsigned long long n) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += stride) {
+    const double v = x[i];
+    double r;
+    switch (fn) {
+      case SS_MATH_FN_LOG10: r = ss::log10_nb(v); break;
+      case SS_MATH_FN_EXP10: r = ss::exp10_nb(v); break;
+      case SS_MATH_FN_ATAN2: r = ss::atan2_nb(v, y2[i]); break;
+      default: r = ss::sqrt_nb(v); break;
+    }
+    out[i] = r;
+  }
+}
+
 // ---------------------------------------------------------------- host side
 struct DevInfo {
   int device = -1, sms = 0, smem_optin = 0;
@@ -1172,6 +1189,18 @@ int ss_ang2pix(int32_t nside, int32_t nest, const double* lon, const double* lat
   int grid, rc;
   if ((rc = small_grid(n, &grid))) return rc;
   k_ang2pix<<<grid, 256, 0, (cudaStream_t)stream>>>(nside, nest, lon, lat, (long long*)pix, n);
+  SS_CUDA(cudaGetLastError());
+  return SS_OK;
+}
+
+int ss_math_probe(int32_t fn, const double* x, const double* y2, double* out, uint64_t n,
+                  void* stream) {
+  if (fn < SS_MATH_FN_LOG10 || fn > SS_MATH_FN_SQRT || !x || !out || (fn == SS_MATH_FN_ATAN2 && !y2))
+    return fail(SS_EINVAL, "ss_math_probe: bad argument%s");
+  if (n == 0) return SS_OK;
+  int grid, rc;
+  if ((rc = small_grid(n, &grid))) return rc;
+  k_math_probe<<<grid, 256, 0, (cudaStream_t)stream>>>(fn, x, y2, out, n);
   SS_CUDA(cudaGetLastError());
   return SS_OK;
 }

@@ -799,6 +799,24 @@ def ang2pix(nside, lon, lat, nest=False, device=None):
     return pix
 
 
+MATH_FN = {"log10": 0, "exp10": 1, "atan2": 2, "sqrt": 3}
+
+
+def math_probe(fn, x, y=None, device=None):
+    """The kernel's own double-precision log10 / 10**x / atan2(x, y) / sqrt, element-wise
+    (``ss_math_probe``); a float64 torch tensor on the device.  Test hook."""
+    torch = _torch()
+    device = require_device(device)
+    lib = _lib.load()
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(np.atleast_1d(a), dtype=np.float64)).to(device)
+    x_t = to(x)
+    y_t = to(y) if y is not None else None
+    out = torch.empty_like(x_t)
+    _small_call(lib.ss_math_probe, device, MATH_FN[fn], x_t.data_ptr(),
+                y_t.data_ptr() if y_t is not None else None, out.data_ptr(), x_t.numel())
+    return out
+
+
 def sample_inverse_cdf(vals, pdf, size, seed=None, u=None, device=None):
     """GPU implementation of ``inverse_transform_sample`` (reference samplers.py:55-76)."""
     from .samplers import inverse_cdf_tables
