@@ -6,8 +6,8 @@ tabulated efficiency / photo-error curves.  The per-star getters
 (``get_maglim``, ``get_extinction``, ``get_photo_error``, ``get_efficiency`` and
 wrappers; reference :173-493) evaluate on the GPU.  ``SurveyFactory`` reproduces
 the YAML-driven loader and cache (:496-1490) for the file formats that can be
-read without healpy/healsparse (``.npy`` maps, CSV curves; FITS/HealSparse maps
-are read through healpy/healsparse only if those packages are installed).
+read without healpy/healsparse (``.npy`` maps, CSV curves; HEALPix FITS and HealSparse
+``.hsp`` maps through the native readers in ``fitsio.py``).
 """
 from __future__ import annotations
 
@@ -470,7 +470,7 @@ class SurveyFactory:
     @staticmethod
     def read_map(path, map_min=None, map_max=None):
         """Dense RING map from ``.npy`` or HEALPix FITS (``.fits``, ``.fits.gz``;
-        native reader, ``fitsio.py``) or ``.hsp`` (needs healsparse).  ``.npy`` and
+        native reader, ``fitsio.py``) or HealSparse ``.hsp`` (native reader too).  ``.npy`` and
         ``.hsp`` maps get UNSEEN -> NaN; FITS maps are returned as ``hp.read_map``
         returns them (reference surveys.py:1019,1117-1118)."""
         lower = path.lower()
@@ -485,9 +485,8 @@ class SurveyFactory:
     @staticmethod
     def open_map_sparse(file_path, **kwargs):
         """HealSparse file -> dense RING map with NaN for unseen pixels (reference :1255-1284)."""
-        import healsparse
-        sparse = healsparse.HealSparseMap.read(file_path)
-        m = sparse.generate_healpix_map(nside=sparse.nside_sparse, nest=False)
+        from .fitsio import read_healsparse_map       # native reader: healsparse not needed
+        m = read_healsparse_map(file_path, nest=False)
         m = np.where(m == hp.UNSEEN, np.nan, m)
         lo, hi = kwargs.get("map_min"), kwargs.get("map_max")
         if lo is not None:

@@ -303,6 +303,39 @@ def test_native_fits_healpix_reader(tmp_path):
         fitsio.read_healpix_map(str(bad))
 
 
+def test_native_healsparse_reader(tmp_path):
+    """``.hsp`` maps (reference surveys.py:1255-1284, healsparse) are read natively: plain
+    and tile-compressed (GZIP_1 / GZIP_2) files, empty coverage pixels, UNSEEN -> NaN and
+    the map_min / map_max clips of ``open_map_sparse``.  No .hsp fixture ships with the
+    reference: round trip through our own writer (parity unpinned, see fitsio.py)."""
+    from stream_sim_b200 import fitsio, healpix as hp
+    from stream_sim_b200.surveys import SurveyFactory
+    rng = np.random.default_rng(3)
+    nside = 64
+    m = np.full(hp.nside2npix(nside), np.nan)
+    idx = rng.choice(m.size, 9000, replace=False)
+    m[idx] = rng.normal(25.0, 0.4, idx.size).astype(np.float32)
+    m[: m.size // 3] = np.nan                       # whole coverage pixels without data
+    seen = ~np.isnan(m)
+    for compress in (None, "GZIP_1", "GZIP_2"):
+        path = str(tmp_path / f"m_{compress}.hsp")
+        fitsio.write_healsparse(path, m, nside_coverage=8, compress=compress)
+        nside_cov, nside_sparse, cov, vals, sentinel = fitsio.read_healsparse(path)
+        assert (nside_cov, nside_sparse, sentinel) == (8, nside, hp.UNSEEN)
+        assert cov.size == hp.nside2npix(8) and vals.size % (nside // 8) ** 2 == 0
+        out = SurveyFactory.read_map(path)
+        assert np.array_equal(np.isnan(out), ~seen)
+        assert np.array_equal(out[seen], m[seen])
+        nest = fitsio.read_healsparse_map(path, nest=True)
+        assert np.array_equal(hp.reorder_nest_to_ring(nest)[seen], m[seen])
+    clipped = SurveyFactory.open_map_sparse(path, map_min=24.8, map_max=25.5)
+    assert np.array_equal(np.isnan(clipped), ~(seen & (m >= 24.8) & (m <= 25.5)))
+    with pytest.raises(ValueError):
+        bad = tmp_path / "bad.hsp"
+        fitsio.write_healpix_map(str(bad), np.zeros(hp.nside2npix(4)))
+        fitsio.read_healsparse(str(bad))
+
+
 def test_frames_and_ud_grade():
     import streamsim_oracle as oracle
     from stream_sim_b200 import healpix as hp
