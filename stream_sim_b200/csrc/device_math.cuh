@@ -257,12 +257,19 @@ __device__ __forceinline__ Guide guide_of(const SSFunc& f, const double* __restr
   return G;
 }
 
+// Guide entries carry two flag bits (engine.BlobPacker.add_bucket_guide): the index is the
+// last knot at or below every x that can land in the bucket; SS_GUIDE_ONE says exactly one
+// more knot can lie at or below such an x, SS_GUIDE_MANY says several can.
+#define SS_GUIDE_ONE 0x80000000u
+#define SS_GUIDE_MANY 0x40000000u
+#define SS_GUIDE_INDEX 0x3fffffffu
+
 // last j in [0, n) with xp[j] <= x; requires xp[0] <= x <= xp[n-1]
 __device__ __forceinline__ int locate(const double* __restrict__ xp, int n, const Guide& G, double x) {
   if (G.n <= 0) return search_le(xp, 0, n, x);
   int b = (int)((x - G.x0) * G.inv);
   b = max(0, min(b, G.n - 1));
-  int j = G.g[b];
+  int j = (int)((unsigned)G.g[b] & SS_GUIDE_INDEX);
   while (j > 0 && xp[j] > x) --j;
   while (j + 1 < n && xp[j + 1] <= x) ++j;
   return j;
@@ -283,11 +290,32 @@ __device__ __forceinline__ double lin_at(const double* __restrict__ xp, const do
 __device__ __forceinline__ double lin_eval(const SSFunc& f, const double* __restrict__ tab,
                                            double x, double fill_lo, double fill_hi) {
   const double* __restrict__ xp = tab + f.x_off;
+  const double* __restrict__ fp = tab + f.c_off;
   const int n = f.n;
+  if (f.g_n > 0) {
+    // guided table (the survey curves): bucket -> knot with at most one compare, the range
+    // and NaN cases as selects against the table ends kept in the descriptor (p[2], p[3]);
+    // no search loop, no loads of xp[0] / xp[n-1]
+    int b = (int)((x - f.g_x0) * f.g_inv);                  // NaN -> 0
+    b = max(0, min(b, f.g_n - 1));
+    const unsigned g = (unsigned)reinterpret_cast<const int32_t*>(tab + f.g_off)[b];
+    int j = (int)(g & SS_GUIDE_INDEX);
+    if (g & SS_GUIDE_MANY) {
+      while (j > 0 && xp[j] > x) --j;
+      while (j + 1 < n && xp[j + 1] <= x) ++j;
+    } else {
+      j += ((g & SS_GUIDE_ONE) && x >= xp[min(j + 1, n - 1)]) ? 1 : 0;
+    }
+    const double xj = xp[j], fj = fp[j];
+    double r = (j == n - 1 || xj == x) ? fj : __dadd_rn(__dmul_rn(fp[n + j], __dsub_rn(x, xj)), fj);
+    r = (x < f.p[2]) ? fill_lo : r;
+    r = (x > f.p[3]) ? fill_hi : r;
+    return (x != x) ? x : r;
+  }
   if (x != x) return x;
   if (x < xp[0]) return fill_lo;
   if (x > xp[n - 1]) return fill_hi;
-  return lin_at(xp, tab + f.c_off, n, locate(xp, n, guide_of(f, tab), x), x);
+  return lin_at(xp, fp, n, search_le(xp, 0, n, x), x);
 }
 
 // scipy CubicSpline(bc_type='natural', extrapolate=False)(x): PPoly in powers of

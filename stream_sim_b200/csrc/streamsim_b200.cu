@@ -383,14 +383,17 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
   const int32_t* sitab = reinterpret_cast<const int32_t*>(stab);
   __syncthreads();
 
-  unsigned c_obs = 0, c_perf = 0, c_bad_g = 0, c_bad_r = 0, c_unseen = 0, c_dom = 0, c_coord = 0,
-           c_tot = 0;
+  // Summary counters go straight to shared memory (uniform-address atomicAdd: REDUX +
+  // one ATOMS per warp) instead of living in eight registers across the whole loop body:
+  // registers, not instructions, are this kernel's scarce resource.
+#define SS_COUNT(slot, cond) \
+  do { if (want_cnt) atomicAdd(&s_cnt[slot], (cond) ? 1u : 0u); } while (0)
 
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n;
        i += stride) {
     const unsigned long long gi = a.offset + i;
-    c_tot++;
+    unsigned c_dom = 0;
     double phi1 = 0, phi2 = 0, dist = ss::nan_d(), mag_g = ss::nan_d(), mag_r = ss::nan_d();
     double ra = 0, dec = 0, wx = 0, wy = 0, wz = 0, lon = 0;
     bool on_grid = false;   // phi1 came from the grid table: row holds f(phi1) values
@@ -477,6 +480,7 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
           mag_r = __dadd_rn(m2, dist);
         }
       }
+      if (c_dom && want_cnt) atomicAdd(&s_cnt[SS_CNT_DOMAIN], c_dom);
       put<OutT>(a.o.phi1, i, phi1);
       put<OutT>(a.o.phi2, i, phi2);
       put<OutT>(a.o.dist, i, dist);
@@ -553,7 +557,7 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
         }
         if (a.o.pix) a.o.pix[i] = ss::hp_pix(L, p.nside_pix, nest);
       } else {
-        c_coord++;
+        if (want_cnt) atomicAdd(&s_cnt[SS_CNT_BADCOORD], 1u);
         if (a.o.pix) a.o.pix[i] = -1;
       }
 
@@ -613,7 +617,7 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
             flag_c = u_det <= ss::efficiency(p, p.completeness, tab, b, mt2[b], maglim);
             if (p.perfect_galstarsep)
               flag_d = u_det2 <= ss::efficiency(p, p.detection, tab, b, mt2[b], maglim);
-            if (maglim != maglim) c_unseen++;
+            SS_COUNT(SS_CNT_UNSEEN, maglim != maglim);
           }
         }
         if (plain) {
@@ -657,7 +661,7 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
           double mobs = mobs2[b];
           if (good && p.dust_correction) mobs = __dsub_rn(mobs, ext2[b]);  // observed.py:194-208
           valid = valid && good;
-          if (!good) { if (b == SS_BAND_G) c_bad_g++; else c_bad_r++; }
+          SS_COUNT(b == SS_BAND_G ? SS_CNT_BADMAG_G : SS_CNT_BADMAG_R, !good);
           if (p.snr_cut[b]) snr_ok = snr_ok && (err2[b] <= p.snr_err_max);   // observed.py:266-281
           if (b == SS_BAND_R) snr_r_ok = (err2[b] <= p.snr_err_max);         // observed.py:283-286
           put<OutT>(a.o.mag_obs[b], i, mobs);
@@ -726,14 +730,14 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
         }
         if (good && p.dust_correction) mobs = __dsub_rn(mobs, ext);    // observed.py:194-208
         valid = valid && good;
-        if (!good) { if (b == SS_BAND_G) c_bad_g++; else c_bad_r++; }
+        SS_COUNT(b == SS_BAND_G ? SS_CNT_BADMAG_G : SS_CNT_BADMAG_R, !good);
         if (p.snr_cut[b]) snr_ok = snr_ok && (err <= p.snr_err_max);   // observed.py:266-281
         if (b == SS_BAND_R) snr_r_ok = (err <= p.snr_err_max);         // observed.py:283-286
         if (b == p.completeness_band) {                                // observed.py:224-243
           flag_c = u_det <= ss::efficiency(p, p.completeness, tab, b, m_true, maglim);
           if (p.perfect_galstarsep)
             flag_d = u_det2 <= ss::efficiency(p, p.detection, tab, b, m_true, maglim);
-          if (maglim != maglim) c_unseen++;
+          SS_COUNT(SS_CNT_UNSEEN, maglim != maglim);
         }
         put<OutT>(a.o.mag_obs[b], i, mobs);
         put<OutT>(a.o.magerr[b], i, err);
@@ -743,8 +747,8 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
       const bool perfect = p.perfect_galstarsep && valid && flag_d && snr_ok && snr_r_ok;
       if (a.o.flag_observed) a.o.flag_observed[i] = observed ? 1 : 0;
       if (a.o.flag_perfect) a.o.flag_perfect[i] = perfect ? 1 : 0;
-      c_obs += observed;
-      c_perf += perfect;
+      SS_COUNT(SS_CNT_OBSERVED, observed);
+      if (p.perfect_galstarsep) SS_COUNT(SS_CNT_PERFECT, perfect);
     }
 
     if (want_hist) {
@@ -758,12 +762,7 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
   }
 
   if (want_cnt) {
-    const unsigned vals[8] = {c_tot, c_obs, c_perf, c_bad_g, c_bad_r, c_unseen, c_dom, c_coord};
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const unsigned s = __reduce_add_sync(0xffffffffu, vals[k]);
-      if ((threadIdx.x & 31) == 0 && s) atomicAdd(&s_cnt[k], s);
-    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&a.o.counters[SS_CNT_TOTAL], a.n);
     __syncthreads();
     for (int k = threadIdx.x; k < SS_N_COUNTERS; k += blockDim.x)
       if (s_cnt[k]) atomicAdd(&a.o.counters[k], (unsigned long long)s_cnt[k]);
@@ -875,9 +874,10 @@ constexpr int kStaticSmem = 8 + 4 * SS_N_COUNTERS + 4 * SS_N_HIST * SS_HIST_BINS
 int plan_launch(const DevInfo& d, int64_t blob_bytes, uint64_t n, int& smem, int& grid) {
   smem = (blob_bytes > 0 && blob_bytes + kStaticSmem <= d.smem_optin) ? (int)blob_bytes : 0;
   const uint64_t blocks_needed = (n + SS_BLOCK - 1) / SS_BLOCK;
-  // one persistent CTA per SM when the blob is large; otherwise as many as fit
+  // persistent CTAs, as many as are resident per SM: a 1024-thread CTA at 64 registers
+  // per thread owns the whole register file, smaller CTAs pair up when shared memory allows
   int per_sm = 1;
-  if (smem + kStaticSmem <= d.smem_optin / 2) per_sm = 2;
+  if (SS_BLOCK <= 512 && smem + kStaticSmem <= d.smem_optin / 2) per_sm = 2;
   const uint64_t cap = (uint64_t)d.sms * per_sm;
   grid = (int)(blocks_needed < cap ? (blocks_needed ? blocks_needed : 1) : cap);
   return SS_OK;

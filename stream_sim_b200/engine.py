@@ -28,6 +28,7 @@ COLUMNS_FLOAT = ("phi1", "phi2", "dist", "mag_g", "mag_r", "ra", "dec",
 GENERATE_COLUMNS = ("phi1", "phi2", "dist", "mag_g", "mag_r")
 ROTATE_COLUMNS = ("ra", "dec")
 SNR_MIN = 5.0            # reference observed.py:267
+GUIDE_ONE, GUIDE_MANY = 1 << 31, 1 << 30      # flag bits of a bucket-guide entry
 CDF_GUIDE = 8192
 IMF_GUIDE = 4096
 ISO_LUT = 1 << 15
@@ -98,8 +99,17 @@ class BlobPacker:
             return dict(g_n=0, g_off=0, g_x0=0.0, g_inv=0.0)
         g_n = 1 << int(np.ceil(np.log2((4.0 if n <= 512 else 1.5) * n)))
         inv = g_n / span
-        edges = xs[0] + np.arange(g_n) / inv
-        guide = np.maximum(np.searchsorted(xs, edges, side="right") - 1, 0).astype(np.int32)
+        # Every x the device can compute into bucket b lies in [edge_b - d, edge_b+1 + d]
+        # (d covers the rounding of (x - x0) * inv at a bucket edge).  guide[b] = last knot
+        # at or below that interval; GUIDE_ONE marks buckets whose interval holds exactly
+        # one more knot (one compare settles it), GUIDE_MANY those with several (scan).
+        d = (abs(xs[0]) + span) * 1e-12
+        lo_edge = xs[0] + np.arange(g_n) / inv - d
+        hi_edge = xs[0] + (np.arange(g_n) + 1) / inv + d
+        base = np.maximum(np.searchsorted(xs, lo_edge, side="right") - 1, 0)
+        inside = np.searchsorted(xs, hi_edge, side="right") - 1 - base
+        flag = np.where(inside == 1, GUIDE_ONE, np.where(inside > 1, GUIDE_MANY, 0))
+        guide = (base.astype(np.int64) | flag).astype(np.uint32).view(np.int32)
         return dict(g_n=g_n, g_off=self.add_ints(guide, dedupe=True), g_x0=float(xs[0]),
                     g_inv=float(inv))
 
@@ -114,7 +124,8 @@ class BlobPacker:
         with np.errstate(divide="ignore", invalid="ignore"):
             slope = (ys[1:] - ys[:-1]) / (xs[1:] - xs[:-1])
         fields = dict(n=len(xs), x_off=self.add_doubles(xs, dedupe=True),
-                      c_off=self.add_doubles(np.concatenate([ys, slope, [0.0]])))
+                      c_off=self.add_doubles(np.concatenate([ys, slope, [0.0]])),
+                      p=(0.0, 0.0, float(xs[0]), float(xs[-1])))   # p[2:4] = table range (lin_eval)
         fields.update(self.add_bucket_guide(xs))
         return fields
 

@@ -147,10 +147,21 @@ def test_blob_packer_layout_and_guides():
     assert np.array_equal(xs, np.sort(x))
     ys = d[f1["c_off"]:f1["c_off"] + 10]
     assert np.array_equal(ys, y[np.argsort(x, kind="mergesort")])       # stable: 2.0 twice keeps order
-    guide = blob.view(np.int32)[2 * f1["g_off"]:2 * f1["g_off"] + f1["g_n"]]
-    edges = f1["g_x0"] + np.arange(f1["g_n"]) / f1["g_inv"]
-    for g, e in zip(guide, edges):
-        assert xs[g] <= e + 1e-12 and (g == len(xs) - 1 or xs[g + 1] > e - 1e-12 or xs[g + 1] == xs[g])
+    from stream_sim_b200.engine import GUIDE_ONE, GUIDE_MANY
+    guide = blob.view(np.uint32)[2 * f1["g_off"]:2 * f1["g_off"] + f1["g_n"]].astype(np.int64)
+    edges = f1["g_x0"] + np.arange(f1["g_n"] + 1) / f1["g_inv"]
+    for b, g in enumerate(guide):
+        j, one, many = g & 0x3fffffff, bool(g & GUIDE_ONE), bool(g & GUIDE_MANY)
+        # every x of the bucket has its knot interval at j (or j+1 if flagged ONE)
+        for x in np.linspace(edges[b], edges[b + 1], 7):
+            true_j = min(np.searchsorted(xs, x, side="right") - 1, len(xs) - 1)
+            if many:
+                assert true_j >= j
+            elif one:
+                assert true_j in (j, j + 1) and (true_j == j + 1) == (x >= xs[j + 1])
+            else:
+                assert true_j == j
+    assert sum(bool(g & GUIDE_MANY) for g in guide) <= 4        # only around the repeated knot
     cs = np.sort(np.random.default_rng(0).uniform(size=1000))
     gd = search_guide(cs, 64)
     for g in range(65):
