@@ -51,9 +51,12 @@ __device__ __forceinline__ void bm32(uint32_t wa, uint32_t wb, double& z0, doubl
   const float c1 = ((float)(~wa) + 0.5f) * 2.3283064365386963e-10f;
   const float l_series = -c1 * (1.0f + c1 * (0.5f + c1 * (0.33333334f + c1 * 0.25f)));
   const float l = (c1 < 0.03f) ? l_series : __logf(y);
-  const float r = sqrtf(-2.0f * l);
-  float s, c;
-  sincospif((float)wb * 4.6566128730773926e-10f, &s, &c);   // angle/pi = 2*wb/2^32
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * l));
+  // angle = 2 pi wb / 2^32, taken modulo 2 pi into [-pi, pi) (wb read as a signed word) where
+  // the MUFU sine / cosine are good to 5e-7 absolute
+  const float ang = (float)(int)wb * 4.6566128730773926e-10f * 3.14159265358979f;
+  const float s = __sinf(ang), c = __cosf(ang);
   z0 = (double)(r * c);
   z1 = (double)(r * s);
 }
