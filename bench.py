@@ -210,7 +210,7 @@ def run_reference(args):
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------ GPU arm
@@ -238,6 +238,8 @@ def run_gpu(args):
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    # host buffers of the end-to-end leg on the GPU's own NUMA node
+    prev_affinity = ssd.bind_host_to_gpu(local)
     eng, survey = build_engine(device, NSIDE, math=args.math)
     n = args.stars
     dtype = args.dtype
@@ -359,7 +361,8 @@ def run_gpu(args):
                      "algorithmic_bytes_per_star": bps, "kernel_ms": kernel_ms},
         "e2e": {"value": e2e_value, "unit": "stars/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "stars_per_step_per_gpu": n_e2e,
-                "api": "ss_generate_observe_host (C ABI, pinned host buffers)"},
+                "api": "ss_generate_observe_host (C ABI, pinned host buffers)",
+                    "host_numa_bound": prev_affinity is not None},
         "gpu_launches": args.steps,
         "clocks": clocks,
     }
@@ -367,6 +370,8 @@ def run_gpu(args):
         mixed["roofline_frac"] = (mixed["value"] / world) * bps / 1e9 / peak
         line["mixed_precision"] = mixed
     if world == 1 and not args.no_cpu:
+        if prev_affinity is not None:
+            os.sched_setaffinity(0, prev_affinity)      # the CPU arm gets every host core
         cores = os.cpu_count() or 1
         maps = {k: v.cpu().numpy() for k, v in (("ebv", survey.ebv_map), ("g", survey.maglim_maps["g"]),
                                                 ("r", survey.maglim_maps["r"]))}
@@ -376,10 +381,30 @@ def run_gpu(args):
                                 "kind": "port",
                                 "sample": f"{sample} stars of the same workload "
                                           f"({chunk_cpu} per call, {cores} forked workers)"}
-    print(json.dumps(line))
+    emit(line)
+
+
+_RESULT_FD = None
+
+
+def emit(line):
+    """The one JSON line, on the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 
 
 def main():
+    global _RESULT_FD
+    # stdout carries exactly one JSON line.  Libraries write there too (NCCL prints its
+    # version banner to fd 1, warnings from forked workers ...): keep the real stdout
+    # aside for the result and point fd 1 at stderr for everything else.
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser(description=__doc__)
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -37,6 +37,35 @@ def init_from_env(backend=None):
     return rank, world, local
 
 
+def bind_host_to_gpu(device_index):
+    """Pin this process to the CPUs next to GPU ``device_index`` (NVML's CPU affinity of
+    the device), so that the pinned host buffers it allocates afterwards land on the GPU's
+    own NUMA node: with one process per GPU the device<->host copies of the ``*_host``
+    entry points then stay off the inter-socket link.  Returns the previous affinity set
+    (pass it to ``os.sched_setaffinity(0, ...)`` to undo), or None if nothing was changed
+    (no NVML, no affinity information, not Linux)."""
+    try:
+        import pynvml
+        import torch
+        prev = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid if not uuid.startswith("GPU-") else uuid).encode())
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= prev
+        if not cpus or cpus == prev:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return prev
+    except Exception:
+        return None
+
+
 def reduce_counters(counters):
     """In-place SUM all-reduce of a counters tensor (int64) over all ranks."""
     import torch.distributed as dist
