@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SS_ABI_VERSION 11
+#define SS_ABI_VERSION 12
 
 /* error codes */
 #define SS_OK 0
@@ -194,6 +194,8 @@ typedef struct SSParams {
   double hist_lo[SS_N_HIST], hist_inv_width[SS_N_HIST];
   int32_t math_mode;        /* SS_MATH_*                                          */
   int32_t iso_lut_n;        /* buckets of SSTables.iso_lut (iso_direct)           */
+  int32_t grid_nthr;        /* SS_DENSITY_GRID: thresholds (= steps - 1) of the u -> index map */
+  int32_t pad2_;
 } SSParams;
 
 typedef struct SSTables {
@@ -206,12 +208,15 @@ typedef struct SSTables {
   const double* cdf_pairs;   /* [cdf_n][2] = (sorted cdf_j, slope_j)              */
   const int32_t* cdf_perm;   /* [cdf_n] original index of sorted entry j; NULL if identity */
   const double* grid;        /* [cdf_n] explicit phi1 grid, or NULL = start + j*step */
-  /* SS_DENSITY_GRID: rows[cdf_n][8] = (thr, x, centre, spread, dm_centre, dm_spread,
-   * sin(radians x), cos(radians x)); thr[k] = smallest u with sample index > k
-   * (thr[cdf_n-1] = +inf), also stored compactly in grid_thr[cdf_n].
+  /* SS_DENSITY_GRID: the sample index of inverse_transform_sample (samplers.py:71-75) is a
+   * step function of u; step s = #{k : thr[k] <= u}, k < grid_nthr.  One row per step plus one
+   * for interp1d's fill value: rows[grid_nthr + 2][8] = (thr[s], x, centre, spread, dm_centre,
+   * dm_spread, sin(radians x), cos(radians x)) with x the phi1 grid value the step maps to (the
+   * index may also step DOWN: non-monotone CDFs of spline densities); rows[grid_nthr + 1] is the
+   * fill row (grid index 0).  grid_thr[grid_nthr + 1] = the thresholds, then +inf.
    * grid_lut[grid_lut_n][2 doubles]: bucket b = [b, b+1)/grid_lut_n of u ->
    * (int32 lo | int32 k << 32 as the bits of the first double, thr[lo] as the second):
-   * lo = sample index at the bucket's left edge, k = thresholds inside the bucket. */
+   * lo = step at the bucket's left edge, k = thresholds inside the bucket. */
   const double* grid_rows;
   const double* grid_lut;
   const double* grid_thr;

@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 # ---- constants mirrored from the header
 STAGE_GENERATE, STAGE_ROTATE, STAGE_OBSERVE = 1, 2, 4
@@ -62,7 +62,7 @@ class SSParams(C.Structure):
         ("photo_error", SSFunc), ("completeness", SSFunc), ("detection", SSFunc),
         ("hist_enable", _i32), ("grid_lut_n", _i32),
         ("hist_lo", _f64 * N_HIST), ("hist_inv_width", _f64 * N_HIST),
-        ("math_mode", _i32), ("iso_lut_n", _i32)]
+        ("math_mode", _i32), ("iso_lut_n", _i32), ("grid_nthr", _i32), ("pad2_", _i32)]
 
 
 class SSTables(C.Structure):

@@ -148,19 +148,24 @@ struct GridRow {
 };
 
 // inverse_transform_sample (reference samplers.py:55-76) as a direct lookup: the
-// sample index rint(interp(u)) is a non-decreasing step function of u, so it equals
-// the number of host-computed exact thresholds <= u.  A uniform table over u gives
-// the index at the bucket's edges; the few thresholds inside the bucket settle it.
+// sample index rint(interp(u)) is a step function of u, so the step a draw falls in is
+// the number of host-computed exact thresholds <= u, and each step has its own row (the
+// index may step down as well as up: non-monotone CDFs).  A uniform table over u gives
+// the step at the bucket's edges; the few thresholds inside the bucket settle it.
 __device__ __forceinline__ bool grid_sample(const KArgs& a, double u, GridRow& row) {
   const SSParams& p = a.p;
-  const int n = p.cdf_n;
   long long idx;
   const double2* __restrict__ rows = reinterpret_cast<const double2*>(a.t.grid_rows);
   if (u != u) return false;
   if (u < 0.0 || u > p.cdf_last) {
-    idx = 0;                                  // interp1d fill_value = 0.0
-  } else if (u >= 1.0) {
-    idx = n - 1;
+    idx = p.grid_nthr + 1;                    // interp1d fill_value = 0.0: the fill row
+  } else if (u >= 1.0) {                      // off the bucket table (never a [0,1) draw)
+    int lo = 0, hi = p.grid_nthr;             // number of thresholds <= u
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(&a.t.grid_thr[mid]) <= u) lo = mid + 1; else hi = mid;
+    }
+    idx = lo;
   } else {
     // One 16-byte table entry per bucket of u: (first index lo, number k of thresholds
     // inside the bucket, thr[lo]).  For k <= 1 (82 % of the stars at 2^17 buckets) the
@@ -968,7 +973,7 @@ int validate(uint32_t st, const SSParams* p, const SSTables* t, const SSMaps* m,
       if ((rc = check_func(p->dist_spread, nd, "distance_modulus.spread"))) return rc;
     }
     if (p->density_kind == SS_DENSITY_GRID) {
-      if (!t->grid_rows || !t->grid_lut || !t->grid_thr || p->cdf_n < 2 || p->grid_lut_n < 1)
+      if (!t->grid_rows || !t->grid_lut || !t->grid_thr || p->grid_nthr < 0 || p->grid_lut_n < 1)
         return fail(SS_EINVAL, "grid density needs grid_rows, grid_lut and grid_thr%s");
     }
     if (p->density_kind == SS_DENSITY_INVCDF) {

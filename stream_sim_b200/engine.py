@@ -164,47 +164,82 @@ def search_guide(sorted_vals, guide_n):
     return np.maximum(np.searchsorted(sorted_vals, edges, side="right") - 1, 0).astype(np.int32)
 
 
-def invcdf_index(cs, u):
-    """Sample index of ``inverse_transform_sample`` for uniforms ``u`` given the
-    sorted (monotone) CDF ``cs``: rint(interp1d(cs, arange, fill_value=0)(u))
-    (reference samplers.py:71-75)."""
+def invcdf_index(cs, u, order=None):
+    """Sample index of ``inverse_transform_sample`` for uniforms ``u`` given the sorted CDF
+    ``cs`` and interp1d's ordering ``order`` (None = identity):
+    rint(interp1d(cs, order, fill_value=0)(u)) (reference samplers.py:71-75)."""
     u = np.asarray(u, dtype=float)
-    y = np.interp(u, cs, np.arange(len(cs), dtype=float))
+    fp = np.arange(len(cs), dtype=float) if order is None else np.asarray(order, dtype=float)
+    y = np.interp(u, cs, fp)
     y = np.where((u < cs[0]) | (u > cs[-1]), 0.0, y)
     return np.rint(y).astype(np.int64)
 
 
-def invcdf_thresholds(cs):
-    """thr[k] = smallest double u in [0, 1] with invcdf_index(u) >= k+1, found by
-    bisection on the bit patterns of the doubles, so that on the device
-    ``index(u) = #{k : thr[k] <= u}`` reproduces the reference arithmetic exactly.
-    Returns None when the index is not a monotone function of u."""
+def invcdf_segments(cs, order=None):
+    """The sample index as an explicit step function of u on [0, 1]: returns ``(thr, val)``
+    with ``index(u) = val[#{k : thr[k] <= u}]`` reproducing the reference arithmetic
+    (``invcdf_index``) exactly, or None if that cannot be established.
+
+    Between two consecutive sorted CDF knots the interpolated value moves monotonically from
+    ``order[j]`` to ``order[j+1]`` (up, or down where interp1d's sort interleaved the grid:
+    spline densities that dip below zero), so its rounding passes through every integer in
+    between; each passage happens at one exact double, found by bisection on the bit
+    patterns of the doubles against the reference arithmetic itself."""
+    cs = np.asarray(cs, dtype=float)
     n = len(cs)
-    k = np.arange(n - 1, dtype=np.int64)
-    f0 = int(invcdf_index(cs, np.zeros(1))[0])
-    lo = np.zeros(n - 1, dtype=np.int64)
-    hi = np.full(n - 1, np.array(1.0).view(np.int64), dtype=np.int64)
-    active = k >= f0
+    fp = np.arange(n, dtype=np.int64) if order is None else np.asarray(order, dtype=np.int64)
+    keep = cs[:-1] < 1.0                                   # u < 1: later intervals are never reached
+    a, b = fp[:-1][keep], fp[1:][keep]
+    steps = np.abs(b - a)
+    total = int(steps.sum())
+    if total > 4 * n + 1024:                               # pathological interleaving: generic path
+        return None
+    j = np.repeat(np.flatnonzero(keep), steps)             # interval of every passage
+    within = np.arange(total) - np.repeat(np.cumsum(steps) - steps, steps)
+    sign = np.repeat(np.sign(b - a), steps)
+    target = np.repeat(a, steps) + sign * (within + 1)     # index value after the passage
+    lo = cs[j].view(np.int64).copy()                       # f(lo) is on the near side
+    hi = cs[j + 1].view(np.int64).copy()
     for _ in range(64):
-        todo = active & (hi - lo > 1)
+        todo = hi - lo > 1
         if not todo.any():
             break
         mid = lo + (hi - lo) // 2
-        ge = invcdf_index(cs, mid.view(np.float64)) >= k + 1
-        hi = np.where(todo & ge, mid, hi)
-        lo = np.where(todo & ~ge, mid, lo)
+        f = invcdf_index(cs, mid.view(np.float64), fp)
+        passed = np.where(sign > 0, f >= target, f <= target)
+        hi = np.where(todo & passed, mid, hi)
+        lo = np.where(todo & ~passed, mid, lo)
     thr = hi.view(np.float64).copy()
-    thr[~active] = 0.0
+    val = np.concatenate([invcdf_index(cs, np.zeros(1), fp), target])
+    if cs[0] > 0.0 and val[0] != fp[0]:                    # fill value 0 below the first knot
+        thr = np.concatenate([[cs[0]], thr])
+        val = np.concatenate([val[:1], [fp[0]], target])
     if np.any(np.diff(thr) < 0):
         return None
     # validate against the reference arithmetic, including the thresholds themselves
     rng = np.random.default_rng(12345)
     probe = np.concatenate([rng.uniform(size=200000), thr, np.nextafter(thr, -1.0),
-                            [0.0, np.nextafter(1.0, 0.0)]])
+                            rng.uniform(thr.min(), min(thr.max(), 1.0), size=50000)
+                            if len(thr) else [], [0.0, np.nextafter(1.0, 0.0)]])
     probe = probe[(probe >= 0.0) & (probe < 1.0)]
-    if not np.array_equal(np.searchsorted(thr, probe, side="right"), invcdf_index(cs, probe)):
+    if not np.array_equal(val[np.searchsorted(thr, probe, side="right")],
+                          invcdf_index(cs, probe, fp)):
         return None
-    return thr
+    return thr, val
+
+
+def invcdf_thresholds(cs):
+    """Monotone case of :func:`invcdf_segments`: thr[k] = smallest u with index(u) >= k+1
+    (0.0 for indices below index(0)); None when the index is not monotone in u."""
+    seg = invcdf_segments(cs)
+    if seg is None:
+        return None
+    thr, val = seg
+    if np.any(np.diff(val) != 1):
+        return None
+    out = np.zeros(len(cs) - 1)
+    out[val[0]:val[0] + len(thr)] = thr
+    return out
 
 
 def snr_error_threshold(snr_min=SNR_MIN):
@@ -311,8 +346,8 @@ class StarEngine:
             self._set_cdf(xg, cs, order)
             p.cdf_guide_off = packer.add_ints(search_guide(cs, CDF_GUIDE))
             p.cdf_guide_n = CDF_GUIDE
-            if self._grid_table and p.cdf_identity and not self.tables.grid:
-                self._set_grid_table(stream, xg, cs)
+            if self._grid_table and not self.tables.grid:
+                self._set_grid_table(stream, xg, cs, order)
         else:
             raise Exception(f"Unrecognized sampler: {type(dens).__name__}")
 
@@ -417,25 +452,29 @@ class StarEngine:
             self.grid = torch.from_numpy(np.ascontiguousarray(xg, dtype=float)).to(self.device)
             self.tables.grid = self.grid.data_ptr()
 
-    def _set_grid_table(self, stream, xg, cs):
-        """SS_DENSITY_GRID: exact index thresholds + one 64-byte row per grid point
-        holding every phi1-only quantity of the generate/rotate stages, evaluated
-        with the host (reference) functions."""
+    def _set_grid_table(self, stream, xg, cs, order):
+        """SS_DENSITY_GRID: the sample index as an exact step function of u (thresholds +
+        one 64-byte row per step holding every phi1-only quantity of the generate/rotate
+        stages, evaluated with the host (reference) functions).  Works for monotone CDFs
+        (one step per grid point) and for the non-monotone ones of spline densities that
+        dip below zero (atlas, phoenix: the index also steps down)."""
         torch = _torch()
-        thr = invcdf_thresholds(cs)
-        if thr is None:
+        seg = invcdf_segments(cs, order)
+        if seg is None:
             return
-        n = len(cs)
+        thr, val = seg
+        idx = np.concatenate([val, [0]])                   # last row: interp1d's fill value 0
+        x = xg[idx]
         with np.errstate(invalid="ignore"):
-            c, s = stream.track.center(xg), stream.track.spread(xg)
+            c, s = stream.track.center(x), stream.track.spread(x)
             if stream.distance_modulus is not None:
-                dc, ds = stream.distance_modulus.center(xg), stream.distance_modulus.spread(xg)
+                dc, ds = stream.distance_modulus.center(x), stream.distance_modulus.spread(x)
             else:
-                dc = ds = np.zeros(n)
-        rad = np.radians(xg)
-        rows = np.stack([np.concatenate([thr, [np.inf]]), xg, c, s, dc, ds, np.sin(rad),
-                         np.cos(rad)], axis=1)
+                dc = ds = np.zeros(len(x))
+        rad = np.radians(x)
         thr_full = np.concatenate([thr, [np.inf]])
+        rows = np.stack([np.concatenate([thr_full, [np.inf]]), x, c, s, dc, ds, np.sin(rad),
+                         np.cos(rad)], axis=1)
         edges = np.searchsorted(thr, np.arange(GRID_LUT + 1) / GRID_LUT, side="right")
         lo, k = edges[:-1].astype(np.int64), np.diff(edges).astype(np.int64)
         lut = np.empty((GRID_LUT, 2), dtype=np.float64)
@@ -448,6 +487,7 @@ class StarEngine:
         self.tables.grid_lut = self.grid_lut.data_ptr()
         self.tables.grid_thr = self.grid_thr.data_ptr()
         self.params.grid_lut_n = GRID_LUT
+        self.params.grid_nthr = len(thr)
         self.params.density_kind = _lib.DENSITY_GRID
 
     def model_tensors(self):

@@ -188,6 +188,38 @@ def test_inverse_cdf_tables_match_scipy_interp1d():
     assert np.array_equal(mine, fn(u))
 
 
+def test_inverse_cdf_step_function_is_exact():
+    """engine.invcdf_segments: index(u) = val[#thr <= u] reproduces rint(interp1d(...)(u))
+    exactly -- for the monotone Pal 5 CDF (one step up per grid point) and for the
+    non-monotone atlas / phoenix spline CDFs (the index also steps down) -- at random
+    draws, densely inside the non-monotone region, at every threshold and at the double
+    just below it."""
+    from stream_sim_b200.engine import invcdf_index, invcdf_segments, invcdf_thresholds
+    from stream_sim_b200.samplers import FileLinearDensityCubicSplineInterpolationSampler as S
+    from stream_sim_b200.samplers import inverse_cdf_tables
+    rng = np.random.default_rng(21)
+    for name in ("atlas", "phoenix"):
+        xg, pdf = S("./data/patrick_2022_splines.csv", name).grid()
+        cs, order = inverse_cdf_tables(xg, pdf)
+        thr, val = invcdf_segments(cs, order)
+        assert np.all(np.diff(thr) >= 0) and len(val) == len(thr) + 1
+        assert (np.diff(val) < 0).sum() > 100, "the index steps down inside the negative-pdf region"
+        assert invcdf_thresholds(cs) is not None      # (monotone helper ignores the ordering)
+        bad = np.flatnonzero(order != np.arange(len(order)))
+        probes = [rng.uniform(size=300000),
+                  rng.uniform(cs[bad.min() - 3], cs[bad.max() + 3], size=300000),
+                  thr[thr < 1.0], np.nextafter(thr[(thr > 0) & (thr < 1.0)], -1.0)]
+        for u in probes:
+            assert np.array_equal(val[np.searchsorted(thr, u, side="right")],
+                                  invcdf_index(cs, u, order)), name
+    # monotone case: steps of +1, thresholds equal to the dedicated helper's
+    pdf = np.abs(np.sin(np.linspace(0, 7, 5000))) + 0.01
+    cs, order = inverse_cdf_tables(np.linspace(-1, 1, 5000), pdf)
+    thr, val = invcdf_segments(cs, order)
+    assert np.all(np.diff(val) == 1) and val[0] == 0 and val[-1] == 4999
+    assert np.array_equal(invcdf_thresholds(cs), thr)
+
+
 # ------------------------------------------------------------------ configuration + survey schema
 def test_configs_parse_and_models_build():
     from stream_sim_b200.model import (BackgroundModel, SplineStreamModel, StreamModel,
