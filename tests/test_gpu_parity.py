@@ -333,6 +333,24 @@ def test_full_size_properties(torch_cuda):
     # unseen pixels: 2 % of the map, so ~2 % of the stars
     assert abs(s["n_unseen"] / n - 0.02) < 0.004
 
+    # BASELINE config 5 (synthetic scaling sweep, 1e9-1e11 stars): 1e10 stars streamed as
+    # counters + histograms only -- in ONE launch (64-bit star indices, 32-bit per-CTA
+    # accumulators), in 2^28-star launches, and as the 8 index ranges 8 GPUs would take
+    # (offset + i runs past 2^32 on 7 of them): all three byte-identical.
+    from stream_sim_b200.distributed import shard_range
+    big = 10_000_000_000
+    one = eng.run_summary(big, seed=seed, chunk=big)
+    chunks = eng.run_summary(big, seed=seed)
+    ranks = eng.new_counters()
+    for r in range(8):
+        lo, hi = shard_range(big, r, 8)
+        eng.run_summary(hi - lo, seed=seed, offset=lo, chunk=hi - lo, counters=ranks)
+    assert torch_cuda.equal(one, chunks) and torch_cuda.equal(one, ranks)
+    sb = eng.summarize(one)
+    assert sb["n_total"] == big and sb["hist_phi1"].sum() == big
+    f_huge = sb["n_observed"] / big
+    assert abs(f_huge - f_big) < 5 * np.sqrt(f_big * (1 - f_big) / n)
+
 
 # ------------------------------------------------------------------ distributions
 def _ks(sample, ref_sorted):
