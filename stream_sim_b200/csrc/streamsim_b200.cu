@@ -152,7 +152,9 @@ struct GridRow {
 // the number of host-computed exact thresholds <= u, and each step has its own row (the
 // index may step down as well as up: non-monotone CDFs).  A uniform table over u gives
 // the step at the bucket's edges; the few thresholds inside the bucket settle it.
-__device__ __forceinline__ bool grid_sample(const KArgs& a, double u, GridRow& row) {
+template <bool PRE>
+__device__ __forceinline__ bool grid_sample(const KArgs& a, double u, GridRow& row,
+                                            double2 pre = make_double2(0.0, 0.0)) {
   const SSParams& p = a.p;
   long long idx;
   const double2* __restrict__ rows = reinterpret_cast<const double2*>(a.t.grid_rows);
@@ -174,7 +176,8 @@ __device__ __forceinline__ bool grid_sample(const KArgs& a, double u, GridRow& r
     // -- a 2 MB table that partly lives in L1 -- beat both 2^15 and 2^20.)
     const double fb = u * (double)p.grid_lut_n;
     const int b = (int)fb;
-    const double2 e = __ldg(&reinterpret_cast<const double2*>(a.t.grid_lut)[b]);
+    // PRE: the bucket entry was fetched at the end of the previous star's iteration
+    const double2 e = PRE ? pre : __ldg(&reinterpret_cast<const double2*>(a.t.grid_lut)[b]);
     const long long packed = __double_as_longlong(e.x);
     const int lo = (int)(packed & 0xffffffffLL), k = (int)(packed >> 32);
     if (k <= 1) {
@@ -236,8 +239,10 @@ __device__ __forceinline__ double invcdf_phi1(const KArgs& a, const int32_t* __r
 // arithmetic) and the device finds the segment with the same one-round-trip bucket table
 // as the phi1 grid: no search loops in shared memory, no division, 100 KB less shared
 // memory.  Rows: (U_k, g_k, dg/du, r_k, dr/du, 0); thr[k] = U_{k+1}.
+template <bool PRE>
 __device__ __forceinline__ void iso_sample_direct(const KArgs& a, double u, double& m1, double& m2,
-                                                  unsigned& domain_err) {
+                                                  unsigned& domain_err,
+                                                  double2 pre = make_double2(0.0, 0.0)) {
   const SSParams& p = a.p;
   if (!(u >= 0.0 && u <= 1.0)) {             // interp1d(bounds_error=True) raises
     domain_err++;
@@ -250,7 +255,7 @@ __device__ __forceinline__ void iso_sample_direct(const KArgs& a, double u, doub
   } else {
     const double fb = u * (double)p.iso_lut_n;
     const int b = (int)fb;
-    const double2 e = __ldg(&reinterpret_cast<const double2*>(a.t.iso_lut)[b]);
+    const double2 e = PRE ? pre : __ldg(&reinterpret_cast<const double2*>(a.t.iso_lut)[b]);
     const long long packed = __double_as_longlong(e.x);
     const int lo = (int)(packed & 0xffffffffLL), k = (int)(packed >> 32);
     if (k <= 1) {
@@ -395,6 +400,23 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
   do { if (want_cnt) atomicAdd(&s_cnt[slot], (cond) ? 1u : 0u); } while (0)
 
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  // LEAN software-pipelines the first look-ups: the position uniforms of the NEXT star and
+  // its two bucket entries (phi1 table, isochrone table) are fetched at the end of an
+  // iteration, where few registers are live, so that their L2 round trip is over when the
+  // next iteration starts.
+  double nx_u1 = 0.0, nx_u2 = 0.0;
+  double2 nx_eg = make_double2(0.0, 0.0), nx_ei = make_double2(0.0, 0.0);
+  auto prepare = [&](unsigned long long star) {
+    const uint4 w = ss::philox_block(a.offset + star, SS_DRAW_BLOCK_POS, a.seed);
+    nx_u1 = ss::u52(w.x, w.y);
+    nx_u2 = ss::u52(w.z, w.w);
+    nx_eg = __ldg(&reinterpret_cast<const double2*>(a.t.grid_lut)[(int)(nx_u1 * (double)p.grid_lut_n)]);
+    nx_ei = __ldg(&reinterpret_cast<const double2*>(a.t.iso_lut)[(int)(nx_u2 * (double)p.iso_lut_n)]);
+  };
+  if (LEAN) {
+    const unsigned long long first = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (first < a.n) prepare(first);
+  }
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n;
        i += stride) {
     const unsigned long long gi = a.offset + i;
@@ -408,7 +430,10 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
     // ------------------------------------------------ generate (model.py:106-157)
     if (ST & SS_STAGE_GENERATE) {
       double u_phi1, u_mass;
-      if (d_u_phi1 && (d_u_mass || !has_iso)) {
+      if (LEAN) {
+        u_phi1 = nx_u1;
+        u_mass = nx_u2;
+      } else if (d_u_phi1 && (d_u_mass || !has_iso)) {
         u_phi1 = d_u_phi1[i];
         u_mass = has_iso ? d_u_mass[i] : 0.0;
       } else {
@@ -422,7 +447,7 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
       if (phi1_given == phi1_given) {
         phi1 = phi1_given;
       } else if (density_kind == SS_DENSITY_GRID) {
-        on_grid = grid_sample(a, u_phi1, row);
+        on_grid = LEAN ? grid_sample<true>(a, u_phi1, row, nx_eg) : grid_sample<false>(a, u_phi1, row);
         phi1 = on_grid ? row.x : ss::nan_d();
       } else if (density_kind == SS_DENSITY_UNIFORM) {
         phi1 = __dadd_rn(__dmul_rn(u_phi1, __dsub_rn(p.density_hi, p.density_lo)), p.density_lo);
@@ -479,7 +504,8 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
         }
         if (has_iso) {
           double m1, m2;
-          if (LEAN || p.iso_direct) iso_sample_direct(a, u_mass, m1, m2, c_dom);
+          if (LEAN) iso_sample_direct<true>(a, u_mass, m1, m2, c_dom, nx_ei);
+          else if (p.iso_direct) iso_sample_direct<false>(a, u_mass, m1, m2, c_dom);
           else iso_sample(p, tab, itab, u_mass, m1, m2, c_dom);
           mag_g = __dadd_rn(m1, dist);
           mag_r = __dadd_rn(m2, dist);
@@ -756,6 +782,7 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
       if (p.perfect_galstarsep) SS_COUNT(SS_CNT_PERFECT, perfect);
     }
 
+    if (LEAN && i + stride < a.n) prepare(i + stride);
     if (want_hist) {
       const double hv[SS_N_HIST] = {phi1, phi2, dist, mag_g, mag_g - mag_r};
 #pragma unroll
