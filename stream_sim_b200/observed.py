@@ -406,6 +406,41 @@ class StreamInjector:
         """Magnitude error -> flux error in Jy."""
         return StreamInjector.magToFlux(mag) * mag_error / 1.0857362
 
+    def plot_stream_in_mask(self, data, mask_type, ebv_threshold=0.2, **kwargs):
+        """Stars over the footprint / depth / dust mask (reference :1078-1134).  The mask is
+        built exactly as for the frame search; drawing needs matplotlib, which is outside
+        the GPU path (``plotting.py`` is out of scope): without it this
+        raises ImportError after the same ValueError checks as the reference.  Returns
+        ``(fig, ax)``; ``output_folder=`` saves ``stream_in_mask.png`` there."""
+        mask = self._create_mask(mask_type, verbose=False, ebv_threshold=ebv_threshold)
+        if mask is None:
+            raise ValueError("Could not create mask. Check mask_type parameter.")
+        try:
+            import matplotlib.pyplot as plt
+        except ImportError as e:
+            raise ImportError("plot_stream_in_mask needs matplotlib, which is not installed; "
+                              "the mask itself is available from _create_mask()") from e
+        ra = np.asarray(data["ra"], dtype=float)
+        dec = np.asarray(data["dec"], dtype=float)
+        pad = 5.0
+        lon = np.linspace(max(ra.min() - pad, 0.0), min(ra.max() + pad, 360.0), 600)
+        lat = np.linspace(max(dec.min() - pad, -90.0), min(dec.max() + pad, 90.0), 400)
+        glon, glat = np.meshgrid(lon, lat)
+        pix = hp.ang2pix(hp.get_nside(mask), glon.ravel(), glat.ravel())
+        inside = np.asarray(mask)[np.asarray(pix)].reshape(glon.shape)
+        fig, ax = plt.subplots(figsize=(8, 5))
+        ax.imshow(inside, origin="lower", aspect="auto", cmap="Greys", alpha=0.35,
+                  extent=(lon[0], lon[-1], lat[0], lat[-1]))
+        ax.scatter(ra, dec, s=1.0, color="tab:red")
+        ax.set_xlabel("RA [deg]")
+        ax.set_ylabel("Dec [deg]")
+        ax.invert_xaxis()
+        folder = kwargs.get("output_folder")
+        if folder:
+            os.makedirs(folder, exist_ok=True)
+            fig.savefig(os.path.join(folder, "stream_in_mask.png"), dpi=150)
+        return fig, ax
+
     @classmethod
     def clear_mask_cache(cls):
         cls.mask_cache.clear()

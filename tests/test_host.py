@@ -379,6 +379,40 @@ def test_native_healsparse_reader(tmp_path):
         fitsio.read_healsparse(str(bad))
 
 
+def test_api_surface_covers_the_reference():
+    """Every public class / function / method of the reference's six path modules exists
+    here with the reference's parameters first, in order (scripts/api_diff.py imports the
+    unmodified reference with its third-party imports stubbed).  Build container only."""
+    import subprocess
+    import sys
+    if not os.path.isdir("/root/reference/stream_sim"):
+        pytest.skip("the reference tree is only present in the build container")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "api_diff.py")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "SIGNATURE ORDER DIFFERS:\n" in r.stdout + "\n" and r.stdout.rstrip().endswith("DIFFERS:")
+
+
+def test_plot_stream_in_mask_error_paths():
+    """reference observed.py:1078-1134: ValueError when no mask can be built; drawing needs
+    matplotlib (absent here: ImportError, after the mask was built on the host)."""
+    import pandas as pd
+    from stream_sim_b200.observed import StreamInjector
+    from stream_sim_b200.surveys import Survey, SurveyFactory
+    sv = Survey.synthetic(16, 16)
+    SurveyFactory._build_coverage_map(sv, verbose=False)
+    inj = StreamInjector(sv)
+    df = pd.DataFrame(dict(ra=[10.0, 11.0], dec=[0.0, 1.0]))
+    with pytest.raises(ValueError, match="Could not create mask"):
+        inj.plot_stream_in_mask(df, None)
+    try:
+        import matplotlib  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError, match="matplotlib"):
+            inj.plot_stream_in_mask(df, ["footprint"])
+
+
 def test_frames_and_ud_grade():
     import streamsim_oracle as oracle
     from stream_sim_b200 import healpix as hp
