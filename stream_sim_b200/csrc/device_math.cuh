@@ -66,8 +66,8 @@ __device__ __forceinline__ void bm32(uint32_t wa, uint32_t wb, double& z0, doubl
 // CUDA library versions are accurate but spell every polynomial coefficient as two
 // 32-bit immediates (two UMOV per DFMA: 12 % of the kernel's issued instructions in the
 // round-1 ncu captures); here the coefficients sit in the constant bank and arrive two
-// per LDCU.128.  All are good to <= 2 ulp on their stated domains (tests/test_gpu_math.py
-// checks them against NumPy through ss_math_probe).
+// per LDCU.128.  Designed for <= 2 ulp on their stated domains; tests/test_gpu_math.py holds
+// them to <= 4 ulp of NumPy (sqrt: <= 1 ulp) through ss_math_probe.
 __constant__ __align__(16) double kSinC[8] = {
     1.0, -1.0 / 6, 1.0 / 120, -1.0 / 5040, 1.0 / 362880, -1.0 / 39916800, 1.0 / 6227020800.0,
     -1.0 / 1307674368000.0};
