@@ -172,7 +172,8 @@ def invcdf_index(cs, u, order=None):
     fp = np.arange(len(cs), dtype=float) if order is None else np.asarray(order, dtype=float)
     y = np.interp(u, cs, fp)
     y = np.where((u < cs[0]) | (u > cs[-1]), 0.0, y)
-    return np.rint(y).astype(np.int64)
+    with np.errstate(invalid="ignore"):                    # NaN CDFs (degenerate pdf) -> garbage,
+        return np.rint(y).astype(np.int64)                 # rejected by the callers' validation
 
 
 def invcdf_segments(cs, order=None):

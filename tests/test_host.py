@@ -170,6 +170,47 @@ def test_blob_packer_layout_and_guides():
     assert 1.0 / e >= 5.0 and not (1.0 / np.nextafter(e, 1.0) >= 5.0)
 
 
+def test_flagged_bucket_guide_fuzz():
+    """The loop-free interval look-up of the survey curves (csrc lin_eval: guide entry, at
+    most one compare) emulated in NumPy against searchsorted, on random / uniform / clustered
+    / near-duplicate knot tables, probed at random points, at every knot and bucket edge and
+    at their neighbouring doubles."""
+    from stream_sim_b200.engine import BlobPacker, GUIDE_MANY, GUIDE_ONE
+    rng = np.random.default_rng(1)
+    for trial in range(60):
+        n = int(rng.integers(8, 600))
+        kind = trial % 5
+        if kind == 0:
+            xs = np.sort(rng.uniform(-10, 2, n))
+        elif kind == 1:
+            xs = np.linspace(-10.4, 1.5, n)
+        elif kind == 2:
+            xs = np.sort(np.r_[rng.uniform(-10, 2, n - 4), [0.5, 0.5, 0.5 + 1e-13, 0.5 - 1e-13]])
+        elif kind == 3:
+            xs = np.sort(np.r_[np.linspace(-10, 0, n // 2), np.linspace(0, 1e-6, n - n // 2)])
+        else:
+            xs = np.cumsum(rng.exponential(1.0, n)) - 5
+        pk = BlobPacker()
+        f = pk.add_linear(xs, rng.normal(size=n))
+        blob = pk.finalize()
+        assert f["g_n"] > 0 and f["p"][2] == xs[0] and f["p"][3] == xs[-1]
+        xp = blob.view(np.float64)[f["x_off"]:f["x_off"] + n]
+        guide = blob.view(np.uint32)[2 * f["g_off"]:2 * f["g_off"] + f["g_n"]].astype(np.int64)
+        edges = f["g_x0"] + np.arange(f["g_n"] + 1) / f["g_inv"]
+        x = np.concatenate([rng.uniform(xp[0], xp[-1], 5000), xp, np.nextafter(xp, -np.inf),
+                            np.nextafter(xp, np.inf), edges, np.nextafter(edges, -np.inf),
+                            np.nextafter(edges, np.inf)])
+        x = x[(x >= xp[0]) & (x <= xp[-1])]
+        b = np.clip(((x - f["g_x0"]) * f["g_inv"]).astype(np.int64), 0, f["g_n"] - 1)
+        g = guide[b]
+        j = g & 0x3fffffff
+        true_j = np.minimum(np.searchsorted(xp, x, side="right") - 1, n - 1)
+        jj = np.where(((g & GUIDE_ONE) != 0) & (x >= xp[np.minimum(j + 1, n - 1)]), j + 1, j)
+        scan = (g & GUIDE_MANY) != 0                 # the device scans: right from any start
+        assert np.all(j[scan] <= true_j[scan] + 1)
+        assert np.array_equal(jj[~scan], true_j[~scan]), (trial, kind)
+
+
 def test_inverse_cdf_tables_match_scipy_interp1d():
     """The (sorted cdf, order) pair reproduces interp1d's stable sort, including the
     non-monotone CDFs of spline densities that dip below zero (atlas, phoenix)."""
@@ -218,6 +259,45 @@ def test_inverse_cdf_step_function_is_exact():
     thr, val = invcdf_segments(cs, order)
     assert np.all(np.diff(val) == 1) and val[0] == 0 and val[-1] == 4999
     assert np.array_equal(invcdf_thresholds(cs), thr)
+
+
+def test_inverse_cdf_step_function_fuzz():
+    """Random pdfs -- positive, with negative stretches (non-monotone CDF), with zeros
+    (duplicate CDF knots), leading / trailing zero tails: invcdf_segments either reproduces
+    the reference index exactly or declines (None -> generic device path); it never raises
+    and never returns a wrong table."""
+    from stream_sim_b200.engine import invcdf_index, invcdf_segments
+    from stream_sim_b200.samplers import inverse_cdf_tables
+    rng = np.random.default_rng(0)
+    ok = 0
+    for trial in range(60):
+        n = int(rng.integers(5, 2000))
+        kind = trial % 6
+        if kind == 0:
+            pdf = rng.uniform(0, 1, n)
+        elif kind == 1:
+            pdf = rng.normal(0.3, 0.5, n)
+        elif kind == 2:
+            pdf = np.where(rng.uniform(size=n) < 0.3, 0.0, rng.uniform(0, 1, n))
+        elif kind == 3:
+            pdf = np.sin(np.linspace(0, 9, n)) + 0.2
+        elif kind == 4:
+            pdf = np.r_[np.zeros(n // 3), rng.uniform(0, 1, n - n // 3)]
+        else:
+            pdf = np.r_[rng.uniform(0, 1, n - n // 4), np.zeros(n // 4)]
+        if pdf.sum() <= 0:
+            pdf = pdf - pdf.sum() / n + 1.0 / n
+        cs, order = inverse_cdf_tables(np.linspace(-1, 1, n), pdf.copy())
+        seg = invcdf_segments(cs, order)
+        if seg is None:
+            continue
+        thr, val = seg
+        inner = thr[(thr > 0) & (thr < 1)]
+        u = np.concatenate([rng.uniform(size=5000), inner, np.nextafter(inner, -1.0)])
+        assert np.array_equal(val[np.searchsorted(thr, u, side="right")],
+                              invcdf_index(cs, u, order)), (trial, kind)
+        ok += 1
+    assert ok >= 30
 
 
 # ------------------------------------------------------------------ configuration + survey schema
