@@ -190,10 +190,10 @@ typedef struct SSParams {
   SSFunc detection;         /* detection-only table, used when perfect_galstarsep */
   /* ---- histograms: bin = floor((v - lo) * inv_width), dropped if outside */
   int32_t hist_enable;
-  int32_t grid_lut_n;       /* SS_DENSITY_GRID: buckets of the u -> index table   */
+  int32_t grid_lut_n;       /* SS_DENSITY_GRID: buckets of the u -> index table (power of two) */
   double hist_lo[SS_N_HIST], hist_inv_width[SS_N_HIST];
   int32_t math_mode;        /* SS_MATH_*                                          */
-  int32_t iso_lut_n;        /* buckets of SSTables.iso_lut (iso_direct)           */
+  int32_t iso_lut_n;        /* buckets of SSTables.iso_lut (iso_direct; power of two) */
   int32_t grid_nthr;        /* SS_DENSITY_GRID: thresholds (= steps - 1) of the u -> index map */
   int32_t pad2_;
 } SSParams;

@@ -1002,6 +1002,8 @@ int validate(uint32_t st, const SSParams* p, const SSTables* t, const SSMaps* m,
     if (p->density_kind == SS_DENSITY_GRID) {
       if (!t->grid_rows || !t->grid_lut || !t->grid_thr || p->grid_nthr < 0 || p->grid_lut_n < 1)
         return fail(SS_EINVAL, "grid density needs grid_rows, grid_lut and grid_thr%s");
+      // u * buckets must be exact for bucket = floor(u * buckets) to agree with the host's edges
+      if (p->grid_lut_n & (p->grid_lut_n - 1)) return fail(SS_EINVAL, "grid_lut_n must be a power of two%s");
     }
     if (p->density_kind == SS_DENSITY_INVCDF) {
       if (!t->cdf_pairs || p->cdf_n < 2) return fail(SS_EINVAL, "inverse-CDF density needs cdf_pairs%s");
@@ -1014,6 +1016,7 @@ int validate(uint32_t st, const SSParams* p, const SSTables* t, const SSMaps* m,
       if (p->iso_direct) {
         if (!t->iso_rows || !t->iso_lut || !t->iso_thr || p->iso_n < 2 || p->iso_lut_n < 1)
           return fail(SS_EINVAL, "direct isochrone lookup needs iso_rows, iso_lut, iso_thr%s");
+        if (p->iso_lut_n & (p->iso_lut_n - 1)) return fail(SS_EINVAL, "iso_lut_n must be a power of two%s");
       } else {
         if (p->iso_n < 2 || p->imf_n < 2) return fail(SS_EINVAL, "isochrone/IMF tables too short%s");
         if (p->imf_guide_n & (p->imf_guide_n - 1))

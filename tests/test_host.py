@@ -131,6 +131,43 @@ def test_functions_match_oracle_and_bounds():
         sampler_factory("nope")
 
 
+def test_c_abi_validates_before_touching_cuda_and_fails_loudly_without_a_gpu():
+    """Argument validation happens before any CUDA call (so it is testable here): bucket
+    counts of the direct look-up tables must be powers of two (u * buckets has to be exact).
+    With valid arguments the call goes on to CUDA and, in this GPU-less container, returns
+    the runtime's error -- there is no CPU fallback behind the ABI."""
+    import ctypes as C
+    lib = _lib.load()
+
+    def attempt(lut_n, iso_lut_n=None):
+        p, t, o = _lib.SSParams(), _lib.SSTables(), _lib.SSOut()
+        p.density_kind, p.grid_nthr, p.grid_lut_n = _lib.DENSITY_GRID, 10, lut_n
+        for f in (p.track_center, p.track_spread, p.dist_center, p.dist_spread):
+            f.kind = _lib.FN_CONSTANT
+        fake = 0x1000                                   # never dereferenced on these paths
+        t.grid_rows = t.grid_lut = t.grid_thr = t.blob = fake
+        t.blob_bytes = 16
+        if iso_lut_n:
+            p.has_iso = p.has_dist = p.iso_direct = 1
+            p.iso_n, p.iso_lut_n = 5, iso_lut_n
+            t.iso_rows = t.iso_lut = t.iso_thr = fake
+        o.phi1 = fake
+        rc = lib.ss_generate(C.byref(p), C.byref(t), None, C.byref(o), C.c_uint64(5),
+                             C.c_uint64(0), C.c_uint64(1), None)
+        return rc, lib.ss_last_error().decode()
+
+    assert attempt(1000) == (-1, "grid_lut_n must be a power of two")
+    assert attempt(1024, 1000) == (-1, "iso_lut_n must be a power of two")
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except ImportError:
+        has_gpu = False
+    if not has_gpu:
+        rc, msg = attempt(1024, 1024)
+        assert rc == -2 and "cuda" in msg.lower()
+
+
 # ------------------------------------------------------------------ packing
 def test_blob_packer_layout_and_guides():
     from stream_sim_b200.engine import BlobPacker, search_guide, snr_error_threshold
