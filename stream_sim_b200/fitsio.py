@@ -212,9 +212,13 @@ def _image_1d(hdr, data):
         cmp_type = str(hdr.get("ZCMPTYPE", "")).strip().upper()
         if cmp_type not in ("GZIP_1", "GZIP_2", "NOCOMPRESS"):
             raise ValueError(f"tile compression '{cmp_type}' is not supported (GZIP_1/GZIP_2 are)")
-        if any(str(hdr.get(f"TTYPE{k}", "")).strip().upper() == "ZSCALE"
-               for k in range(1, hdr["TFIELDS"] + 1)):
-            raise ValueError("quantised (lossy) float compression is not supported")
+        # Lossless float compression (ZQUANTIZ = 'NONE', what healsparse writes) keeps the
+        # tile bytes in COMPRESSED_DATA.  Quantised files keep scaled integers there and fall
+        # back to GZIP_COMPRESSED_DATA for tiles that could not be quantised: only the
+        # former need ZSCALE / ZZERO, and those are refused tile by tile below.
+        quantised = (dt.kind == "f" and str(hdr.get("ZQUANTIZ", "NONE")).strip().upper() != "NONE"
+                     and any(str(hdr.get(f"TTYPE{k}", "")).strip().upper() == "ZSCALE"
+                             for k in range(1, hdr["TFIELDS"] + 1)))
         nrows, rowbytes = hdr["NAXIS2"], hdr["NAXIS1"]
         heap0 = hdr.get("THEAP", nrows * rowbytes)
         # column layout: variable-length descriptors 'P' (2 x int32) or 'Q' (2 x int64)
@@ -243,6 +247,8 @@ def _image_1d(hdr, data):
                 nb, ho = int(desc[0]), int(desc[1])
                 if nb == 0:
                     continue
+                if quantised and name == "COMPRESSED_DATA":
+                    raise ValueError("quantised (lossy) float tile compression is not supported")
                 chunk = data[heap0 + ho: heap0 + ho + nb * (1 if name != "UNCOMPRESSED_DATA" else dt.itemsize)]
                 if name == "UNCOMPRESSED_DATA" or cmp_type == "NOCOMPRESS":
                     raw, shuffled = chunk, False
