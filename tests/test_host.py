@@ -437,6 +437,40 @@ def test_survey_factory_loads_npy_survey(tmp_path):
         sv.get_maglim("i")
 
 
+def test_shipped_lsst_config_loads_hsp_and_fits_natively(tmp_path):
+    """config/surveys/lsst_yr1.yaml as shipped (HealSparse depth maps + a HEALPix FITS dust
+    map + the two CSV curves), pointed at a directory holding synthetic files of those names:
+    the YAML-driven loader (reference surveys.py:891-1148) goes through the native .hsp and
+    FITS readers -- neither healsparse nor healpy is installed here."""
+    import pandas as pd
+    import yaml
+    from stream_sim_b200 import fitsio, healpix as hp, synthetic as syn
+    from stream_sim_b200.surveys import Survey, SurveyFactory
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "config", "surveys", "lsst_yr1.yaml")))
+    files = cfg["survey_files"]
+    files["file_path"] = str(tmp_path)
+    ml_g, ml_r, ebv = (syn.healpix_map(k, 32) for k in ("maglim_g", "maglim_r", "ebv"))
+    fitsio.write_healsparse(str(tmp_path / files["maglim_map_g"]), ml_g, nside_coverage=8)
+    fitsio.write_healsparse(str(tmp_path / files["maglim_map_r"]), ml_r, nside_coverage=8,
+                            compress="GZIP_1")
+    fitsio.write_healpix_map(str(tmp_path / files["ebv_map"]), ebv, dtype=np.float64)
+    pd.DataFrame(syn.efficiency_csv_columns()).to_csv(tmp_path / files["completeness"], index=False)
+    pd.DataFrame(syn.photo_error_csv_columns()).to_csv(tmp_path / files["log_photo_error"], index=False)
+    SurveyFactory.clear_cache(verbose=False)
+    sv = Survey.load("lsst", "yr1", config_file=cfg, verbose=False)
+    for got, want in ((sv.maglim_maps["g"], ml_g), (sv.maglim_maps["r"], ml_r)):
+        # .hsp depth maps are clipped at the saturation magnitude (reference :1013-1016)
+        ok = ~np.isnan(want) & (want >= 16.0)
+        assert np.array_equal(np.isnan(got), ~ok)
+        assert np.array_equal(got[ok], want[ok].astype(np.float32))      # .hsp stores float32
+    assert np.array_equal(np.asarray(sv.ebv_map), ebv)
+    assert sorted(sv.bands) == sorted(["u", "g", "r", "i", "z", "y"]) and sv.completeness_band == "r"
+    assert sv.coeff_extinc["r"] == 2.70136780871597 and sv.delta_saturation == -10.4
+    assert sv.completeness is not None and sv.log_photo_error is not None
+    assert hp.get_nside(sv.coverage) == 32
+    SurveyFactory.clear_cache(verbose=False)
+
+
 def test_native_fits_healpix_reader(tmp_path):
     """Survey ingestion without healpy: HEALPix BINTABLE files, RING/NESTED,
     1 or 1024 pixels per row, float32/float64, gzip."""
