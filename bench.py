@@ -248,9 +248,10 @@ def run_gpu(args):
     bps = BYTES_PER_STAR[dtype]
 
     def step(k):
+        # counters accumulate LOCALLY; the one collective of the path (SUM all-reduce of the
+        # 10 KB counter block) runs once, after the timed region
         eng.generate_observe(n, seed=args.seed, offset=(k * world + rank) * n, counters=counters,
                              dtype=dtype, out=out)
-        ssd.reduce_counters(counters)
 
     def barrier():
         if world > 1:
@@ -273,7 +274,6 @@ def run_gpu(args):
         eng.generate_observe(n, seed=args.seed, offset=((args.warmup + k) * world + rank) * n,
                              counters=counters, dtype=dtype, out=out)
         ev[3 + 2 * k].record()
-        ssd.reduce_counters(counters)
     ev[1].record()
     barrier()
     t_wall1 = time.time()
@@ -281,7 +281,12 @@ def run_gpu(args):
     kernel_ms = float(np.mean([ev[2 + 2 * k].elapsed_time(ev[3 + 2 * k]) for k in range(args.steps)]))
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     value = world * n * args.steps / (total_ms * 1e-3)
-    summary = eng.summarize(counters)
+    total = ssd.reduce_counters(counters.clone())       # reduce ONCE, into a copy
+    summary = eng.summarize(total)
+    expect_total = world * n * (args.warmup + args.steps)
+    if summary["n_total"] != expect_total or not (0 < summary["n_observed"] < summary["n_total"]):
+        raise SystemExit(f"counter check failed: n_total {summary['n_total']} (expected "
+                         f"{expect_total}), n_observed {summary['n_observed']}")
 
     # ---- supplementary: the mixed-precision kernel on the same workload (not the headline)
     mixed = None
@@ -354,6 +359,7 @@ def run_gpu(args):
                          "rewritten every step; map/table gathers are L2-resident by design"
                          % (n * bps / 1e9),
                    "parallelism": f"stars sharded over {world} GPU(s), maps replicated",
+                   "n_total": summary["n_total"], "n_observed": summary["n_observed"],
                    "observed_fraction": summary["n_observed"] / max(1, summary["n_total"])},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None if traffic is None else traffic * n,

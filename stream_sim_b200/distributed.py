@@ -67,7 +67,11 @@ def bind_host_to_gpu(device_index):
 
 
 def reduce_counters(counters):
-    """In-place SUM all-reduce of a counters tensor (int64) over all ranks."""
+    """In-place SUM all-reduce of a counters tensor (int64) over all ranks.
+
+    Call it ONCE per run on locally accumulated counters (or on a clone): reducing a
+    running total in place and then accumulating into it again multiplies the earlier
+    steps by the world size at every further reduction."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(counters, op=dist.ReduceOp.SUM)
@@ -87,13 +91,17 @@ def max_over_ranks(value, device=None):
 
 
 def generate_observe_sharded(engine, n_total, seed=0, counters=None, **kw):
-    """Run the fused path for this rank's share of ``n_total`` stars and reduce
-    the counters.  Returns (columns of the local shard, (lo, hi))."""
+    """Run the fused path for this rank's share of ``n_total`` stars and add the
+    GLOBAL (all-rank) counters of this call to ``counters``.  The launch accumulates into
+    a fresh local block which is reduced once and then added, so a ``counters`` tensor
+    that is reused across calls stays a correct global running total on every rank.
+    Returns (columns of the local shard, (lo, hi))."""
     import torch.distributed as dist
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
     lo, hi = shard_range(n_total, rank, world)
-    out = engine.generate_observe(hi - lo, seed=seed, offset=lo, counters=counters, **kw)
+    local = engine.new_counters() if counters is not None else None
+    out = engine.generate_observe(hi - lo, seed=seed, offset=lo, counters=local, **kw)
     if counters is not None:
-        reduce_counters(counters)
+        counters += reduce_counters(local)
     return out, (lo, hi)
