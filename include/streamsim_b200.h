@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SS_ABI_VERSION 12
+#define SS_ABI_VERSION 13
 
 /* error codes */
 #define SS_OK 0
@@ -75,31 +75,37 @@ extern "C" {
 #define SS_BAND_R 1
 
 /* arithmetic of the transcendental-heavy steps (SSParams.math_mode) */
-#define SS_MATH_F64 0   /* everything in double: parity grade                          */
-#define SS_MATH_MIXED 1 /* fp32 Box-Muller / 10^x / sqrt / log with double fallback near
-                           decision thresholds: identical pix and flags, mags ~1e-6 rel. */
+#define SS_MATH_F64 0   /* every value in double (<= 1e-9 of the oracle)               */
+#define SS_MATH_FAST 1  /* same decisions, same positions and true magnitudes; the VALUES of
+                           magerr_b / mag_b_obs come from fp32 10^x / sqrt / log2 (MUFU), with
+                           a per-star double redo when the noisy flux is within a guard band
+                           of zero.  pix and every flag are identical to SS_MATH_F64 (all
+                           comparisons stay in double, the SNR cut is decided on log10(err));
+                           magerr, mag_obs agree to ~2e-6 relative (north star: 1e-5).     */
 
 /* output element type of the floating-point columns */
 #define SS_DTYPE_F64 0
 #define SS_DTYPE_F32 1
 
 /* Philox4x32-10 draw blocks: counter = (star_lo, star_hi, block, 0),
- * key = (seed_lo, seed_hi), output words (w0,w1,w2,w3).
- *   U52(a,b) = ((a >> 12) * 2^32 + b) * 2^-52   (52-bit uniform in [0,1))
- *   U32(a)   = a * 2^-32
+ * key = (seed_lo, seed_hi), output words (w0,w1,w2,w3).  Two blocks per star:
+ *   U32(a)   = a * 2^-32                       (uniform in [0,1), exact in double)
  *   BM32(a,b): fp32 Box-Muller, radius from y = (a+0.5)/2^32, angle 2*pi*b/2^32
- *   block 0: u_phi1 = U52(w0,w1), u_mass = U52(w2,w3)
- *   block 1: (z_phi2, z_dist) = BM32(w0,w1)  [Uniform samplers: U32(w0), U32(w1)],
- *            (z_r, z_g) = BM32(w2,w3)        flux noise
- *   block 2: u_det = U52(w0,w1) (completeness), u_det2 = U52(w2,w3) (detection-only)
- *   block 3: z_phi1 = BM32(w0,w1).first      (Gaussian density only)
+ *   block 0 (POS): u_phi1 = U32(w0), u_mass = U32(w1),
+ *                  (z_phi2, z_dist) = BM32(w2,w3)   [Uniform samplers: U32(w2), U32(w3)]
+ *   block 1 (OBS): (z_r, z_g) = BM32(w0,w1) flux noise,
+ *                  u_det = U32(w2) (completeness), u_det2 = U32(w3) (detection-only)
+ *   block 3:       z_phi1 = BM32(w0,w1).first      (Gaussian density only)
+ * Every uniform decides a table step or a Bernoulli trial; 32 bits resolve both far
+ * below what any test can see (an inverse-CDF step of the 10^5-point grid spans ~4*10^4
+ * values), the bucket of a power-of-two look-up table is a shift of the word, and one
+ * Philox block serves four draws.
  * The normals are random draws, generated in fp32 like cuRAND's curand_normal;
  * everything computed from them is double.  A star's draws depend only on
  * (seed, global star index): any sharding of the index range over launches or
  * GPUs gives identical per-star results.  SSOut.draws_out exports the draws used. */
 #define SS_DRAW_BLOCK_POS 0
-#define SS_DRAW_BLOCK_NORMAL 1
-#define SS_DRAW_BLOCK_DETECT 2
+#define SS_DRAW_BLOCK_OBS 1
 #define SS_DRAW_BLOCK_DENSITY_Z 3
 /* rows of SSOut.draws_out */
 #define SS_DRAW_U_PHI1 0
@@ -183,19 +189,27 @@ typedef struct SSParams {
   double coeff_extinc[2], saturation[2], sys_error[2];
   double delta_saturation;
   double snr_err_max;       /* largest e with fl(1/e) >= SNR_min (observed.py:267-279) */
+  /* the same cut decided on x = log10(statistical error): magerr(x) = sqrt((10**x)**2 + sys**2)
+   * is monotone, so 1/magerr >= SNR_min  <=>  x <= snr_loge_max[b], the largest double for
+   * which the REFERENCE arithmetic (NumPy on the host) passes; saturated stars carry the
+   * constant error err_bright, whose verdict is snr_bright_ok[b] */
+  double snr_loge_max[2];
+  int32_t snr_bright_ok[2];
   double log_err_at_dsat;   /* f(dsat)          surveys.py:278                    */
   double err_bright;        /* 10**f(dsat-1)    surveys.py:284                    */
   SSFunc photo_error;       /* SS_FN_LINEAR, fill 1.0 both sides (surveys.py:1412-1417) */
   SSFunc completeness;      /* SS_FN_LINEAR, fill 0.0           (surveys.py:1361-1366) */
   SSFunc detection;         /* detection-only table, used when perfect_galstarsep */
-  /* ---- histograms: bin = floor((v - lo) * inv_width), dropped if outside */
+  /* ---- histograms, binned in fp32: t = ((float)v - (float)lo) * (float)inv_width (two
+   * roundings, no FMA), bin = (int)t if 0 <= t < SS_HIST_BINS, dropped otherwise */
   int32_t hist_enable;
   int32_t grid_lut_n;       /* SS_DENSITY_GRID: buckets of the u -> index table (power of two) */
   double hist_lo[SS_N_HIST], hist_inv_width[SS_N_HIST];
   int32_t math_mode;        /* SS_MATH_*                                          */
   int32_t iso_lut_n;        /* buckets of SSTables.iso_lut (iso_direct; power of two) */
   int32_t grid_nthr;        /* SS_DENSITY_GRID: thresholds (= steps - 1) of the u -> index map */
-  int32_t pad2_;
+  int32_t fused_kernel;     /* 1 (default): the production launch may take the pipelined kernel
+                               k_fused; 0: always the generic k_stars (tests compare the two) */
 } SSParams;
 
 typedef struct SSTables {
@@ -213,7 +227,9 @@ typedef struct SSTables {
    * for interp1d's fill value: rows[grid_nthr + 2][8] = (thr[s], x, centre, spread, dm_centre,
    * dm_spread, sin(radians x), cos(radians x)) with x the phi1 grid value the step maps to (the
    * index may also step DOWN: non-monotone CDFs of spline densities); rows[grid_nthr + 1] is the
-   * fill row (grid index 0).  grid_thr[grid_nthr + 1] = the thresholds, then +inf.
+   * fill row (grid index 0).  Column 0 is free for the host: its low 32 bits hold the phi1
+   * histogram bin of x (int32, -1 = outside), so the production kernel never bins phi1.
+   * grid_thr[grid_nthr + 1] = the thresholds, then +inf.
    * grid_lut[grid_lut_n][2 doubles]: bucket b = [b, b+1)/grid_lut_n of u ->
    * (int32 lo | int32 k << 32 as the bits of the first double, thr[lo] as the second):
    * lo = step at the bucket's left edge, k = thresholds inside the bucket. */
@@ -232,7 +248,12 @@ typedef struct SSMaps {
   const double* ebv;         /* [12*nside_ebv^2]                                  */
   const double* maglim[2];   /* [12*nside_maglim[b]^2], NaN = unseen              */
   const uint8_t* mask;       /* ss_frame_fraction only: [12*nside_mask^2]         */
-  int32_t nside_mask, pad_;
+  int32_t nside_mask;
+  /* optional: the three maps interleaved, [12*nside_packed^2][4] = (ebv, maglim_g,
+   * maglim_r, 0) -- one 32-byte sector per star instead of three gathers.  Only valid
+   * when the three maps share one nside (0 = absent). */
+  int32_t nside_packed;
+  const double* packed;
 } SSMaps;
 
 typedef struct SSCatalog {   /* per-star inputs of the stages that are not run */
@@ -323,6 +344,24 @@ int ss_ang2pix(int32_t nside, int32_t nest, const double* lon_deg, const double*
 #define SS_MATH_FN_SQRT 3
 int ss_math_probe(int32_t fn, const double* x, const double* y2, double* out, uint64_t n,
                   void* stream);
+
+/* Stand-alone pieces of the path, element-wise on device arrays (the reference exposes them
+ * as public methods; inside ss_generate_observe the same arithmetic is fused).
+ *  ss_loc_scale: out = draw * scale + loc, scipy's rv.rvs(loc, scale) (samplers.py:94-138).
+ *    loc / scale: per-element arrays or NULL = the scalars loc0 / scale0; draws: injected
+ *    standard draws or NULL = the star's own z_phi2 (normal != 0) / u_phi2 (Philox POS block).
+ *  ss_noisy_magnitudes: StreamInjector.sample_measured_magnitudes (observed.py:863-904) as
+ *    written (flux-space noise); NaN where the reference writes "BAD_MAG"; z injected or the
+ *    star's z_r.
+ *  ss_bernoulli: out = (u <= prob), StreamInjector.detect_flag's trial (observed.py:906-959);
+ *    u injected or the star's u_det. */
+int ss_loc_scale(int32_t normal, const double* loc, const double* scale, double loc0,
+                 double scale0, const double* draws, double* out, uint64_t n, uint64_t star_offset,
+                 uint64_t seed, void* stream);
+int ss_noisy_magnitudes(const double* mag, const double* err, const double* z, double* out,
+                        uint64_t n, uint64_t star_offset, uint64_t seed, void* stream);
+int ss_bernoulli(const double* prob, const double* u, uint8_t* out, uint64_t n,
+                 uint64_t star_offset, uint64_t seed, void* stream);
 
 /* Host-buffer variant of ss_generate_observe: every SSOut column pointer (and
  * counters) is a HOST pointer (pinned for full speed).  Stars are produced in

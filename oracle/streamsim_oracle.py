@@ -64,13 +64,6 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return c0, c1, c2, c3
 
 
-def _u52(a, b):
-    """Two 32-bit words -> double in [0,1) with 52 random bits (the device builds
-    the mantissa of a double in [1,2) from them and subtracts 1)."""
-    return ((a >> np.uint32(12)).astype(np.float64) * 4294967296.0
-            + b.astype(np.float64)) * (1.0 / 4503599627370496.0)
-
-
 def philox_block(seed, index, block):
     """The four 32-bit words of draw-block ``block`` for global star ``index``.
 
@@ -107,21 +100,22 @@ def bm32(wa, wb):
 
 
 def device_draws(seed, start, n):
-    """All per-star draws the kernel derives for stars [start, start+n).
+    """All per-star draws the kernel derives for stars [start, start+n): two Philox blocks
+    per star, layout of include/streamsim_b200.h (SS_DRAW_BLOCK_POS / _OBS).
 
     Returns the dict accepted by :func:`generate` / :func:`observe`.  The uniforms
-    (u_phi1, u_mass, u_phi2, u_dist, u_det, u_det2) are exactly the device's; the
-    normals (z_phi2, z_dist, z_r, z_g) are the float32 emulation of :func:`bm32`.
+    (u_phi1, u_mass, u_phi2, u_dist, u_det, u_det2; one 32-bit word each) are exactly the
+    device's; the normals (z_phi2, z_dist, z_r, z_g) are the float32 emulation of
+    :func:`bm32`.
     """
     idx = np.arange(start, start + n, dtype=np.uint64)
     w = philox_block(seed, idx, 0)
-    u_phi1, u_mass = _u52(w[0], w[1]), _u52(w[2], w[3])
+    u_phi1, u_mass = _u32(w[0]), _u32(w[1])
+    z_phi2, z_dist = bm32(w[2], w[3])
+    u_phi2, u_dist = _u32(w[2]), _u32(w[3])
     w = philox_block(seed, idx, 1)
-    z_phi2, z_dist = bm32(w[0], w[1])
-    z_r, z_g = bm32(w[2], w[3])
-    u_phi2, u_dist = _u32(w[0]), _u32(w[1])
-    w = philox_block(seed, idx, 2)
-    u_det, u_det2 = _u52(w[0], w[1]), _u52(w[2], w[3])
+    z_r, z_g = bm32(w[0], w[1])
+    u_det, u_det2 = _u32(w[2]), _u32(w[3])
     return dict(u_phi1=u_phi1, u_mass=u_mass, u_phi2=u_phi2, u_dist=u_dist,
                 z_phi2=z_phi2, z_dist=z_dist, z_r=z_r, z_g=z_g,
                 u_det=u_det, u_det2=u_det2)

@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 # ---- constants mirrored from the header
 STAGE_GENERATE, STAGE_ROTATE, STAGE_OBSERVE = 1, 2, 4
@@ -19,7 +19,7 @@ DENSITY_UNIFORM, DENSITY_INVCDF, DENSITY_GAUSSIAN, DENSITY_NONE, DENSITY_GRID = 
 BAND_G, BAND_R = 0, 1
 BAND_INDEX = {"g": BAND_G, "r": BAND_R}
 DTYPE_F64, DTYPE_F32 = 0, 1
-MATH_F64, MATH_MIXED = 0, 1
+MATH_F64, MATH_FAST = 0, 1
 (CNT_TOTAL, CNT_OBSERVED, CNT_PERFECT, CNT_BADMAG_G, CNT_BADMAG_R, CNT_UNSEEN, CNT_DOMAIN,
  CNT_BADCOORD, CNT_INSIDE) = range(9)
 N_COUNTERS, HIST_BINS, N_HIST = 16, 256, 5
@@ -58,11 +58,12 @@ class SSParams(C.Structure):
         ("nest", _i32),
         ("coeff_extinc", _f64 * 2), ("saturation", _f64 * 2), ("sys_error", _f64 * 2),
         ("delta_saturation", _f64), ("snr_err_max", _f64),
+        ("snr_loge_max", _f64 * 2), ("snr_bright_ok", _i32 * 2),
         ("log_err_at_dsat", _f64), ("err_bright", _f64),
         ("photo_error", SSFunc), ("completeness", SSFunc), ("detection", SSFunc),
         ("hist_enable", _i32), ("grid_lut_n", _i32),
         ("hist_lo", _f64 * N_HIST), ("hist_inv_width", _f64 * N_HIST),
-        ("math_mode", _i32), ("iso_lut_n", _i32), ("grid_nthr", _i32), ("pad2_", _i32)]
+        ("math_mode", _i32), ("iso_lut_n", _i32), ("grid_nthr", _i32), ("fused_kernel", _i32)]
 
 
 class SSTables(C.Structure):
@@ -73,7 +74,7 @@ class SSTables(C.Structure):
 
 class SSMaps(C.Structure):
     _fields_ = [("ebv", _vp), ("maglim", _vp * 2), ("mask", _vp), ("nside_mask", _i32),
-                ("pad_", _i32)]
+                ("nside_packed", _i32), ("packed", _vp)]
 
 
 class SSCatalog(C.Structure):
@@ -116,6 +117,9 @@ SYMBOLS = {
     "ss_eval_function": (C.c_int, [_P(SSFunc), _P(SSTables), _vp, _vp, _u64, _vp]),
     "ss_ang2pix": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _u64, _vp]),
     "ss_math_probe": (C.c_int, [_i32, _vp, _vp, _vp, _u64, _vp]),
+    "ss_loc_scale": (C.c_int, [_i32, _vp, _vp, _f64, _f64, _vp, _vp, _u64, _u64, _u64, _vp]),
+    "ss_noisy_magnitudes": (C.c_int, [_vp, _vp, _vp, _vp, _u64, _u64, _u64, _vp]),
+    "ss_bernoulli": (C.c_int, [_vp, _vp, _vp, _u64, _u64, _u64, _vp]),
     "ss_host_workspace_bytes": (_i64, [_u64, _i32]),
     "ss_generate_observe_host": (C.c_int, [_P(SSParams), _P(SSTables), _P(SSMaps), _P(SSOut),
                                            _u64, _u64, _u64, _vp, _i64, _u64]),

@@ -9,6 +9,11 @@
 #include <stdint.h>
 #include "../../include/streamsim_b200.h"
 
+// rare per-star paths: out of line (__noinline__) or inline in a cold branch
+#ifndef SS_COLD
+#define SS_COLD __forceinline__
+#endif
+
 namespace ss {
 
 __device__ __forceinline__ double nan_d() { return __longlong_as_double(0x7ff8000000000000LL); }
@@ -38,15 +43,21 @@ __device__ __forceinline__ uint4 philox_block(unsigned long long star, uint32_t 
   return philox4x32_10(c, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
 }
 
-// one 32-bit word -> double in [0,1), exact
-__device__ __forceinline__ double u32(uint32_t w) { return (double)w * (1.0 / 4294967296.0); }
+// one 32-bit word -> the double w (exact): the word becomes the low mantissa bits of 2^52
+// (one DADD, no I2F)
+__device__ __forceinline__ double word_to_double(uint32_t w) {
+  return __hiloint2double(0x43300000, (int)w) - 4503599627370496.0;
+}
+
+// one 32-bit word -> double in [0,1), exact: w * 2^-32
+__device__ __forceinline__ double u32(uint32_t w) { return word_to_double(w) * (1.0 / 4294967296.0); }
 
 // Box-Muller from two 32-bit words, evaluated in fp32 (like cuRAND's curand_normal): the
 // draw is a random number, not a quantity with a parity requirement, and everything
 // computed *from* it downstream stays in double.  y = (wa+0.5)/2^32 in (0,1) feeds the
 // radius; for y close to 1 the complement (~wa+0.5)/2^32 = 1-y is exact and a short
 // series replaces log(y), which would lose relative accuracy there.  |z| <= 6.7.
-__device__ __forceinline__ void bm32(uint32_t wa, uint32_t wb, double& z0, double& z1) {
+__device__ __forceinline__ void bm32f(uint32_t wa, uint32_t wb, float& z0, float& z1) {
   const float y = ((float)wa + 0.5f) * 2.3283064365386963e-10f;
   const float c1 = ((float)(~wa) + 0.5f) * 2.3283064365386963e-10f;
   const float l_series = -c1 * (1.0f + c1 * (0.5f + c1 * (0.33333334f + c1 * 0.25f)));
@@ -57,8 +68,15 @@ __device__ __forceinline__ void bm32(uint32_t wa, uint32_t wb, double& z0, doubl
   // the MUFU sine / cosine are good to 5e-7 absolute
   const float ang = (float)(int)wb * 4.6566128730773926e-10f * 3.14159265358979f;
   const float s = __sinf(ang), c = __cosf(ang);
-  z0 = (double)(r * c);
-  z1 = (double)(r * s);
+  z0 = r * c;
+  z1 = r * s;
+}
+
+__device__ __forceinline__ void bm32(uint32_t wa, uint32_t wb, double& z0, double& z1) {
+  float a, b;
+  bm32f(wa, wb, a, b);
+  z0 = (double)a;
+  z1 = (double)b;
 }
 
 // ---------------------------------------------------------------- elementary functions
@@ -290,31 +308,49 @@ __device__ __forceinline__ double lin_at(const double* __restrict__ xp, const do
   return __dadd_rn(__dmul_rn(fp[n + j], __dsub_rn(x, xj)), fj);
 }
 
+// The guided look-up of a LINEAR table in two halves, so that curves tabulated on the same
+// abscissae (the survey's photo-error and efficiency curves) are located once per star.
+__device__ __forceinline__ int lin_locate(const SSFunc& f, const double* __restrict__ tab, double x) {
+  const double* __restrict__ xp = tab + f.x_off;
+  const int n = f.n;
+  if (f.g_n <= 0) {                                        // tiny table without a guide
+    if (!(x >= xp[0])) return 0;                           // below, or NaN: lin_value fills
+    return (x >= xp[n - 1]) ? n - 1 : search_le(xp, 0, n, x);
+  }
+  // bucket -> knot with at most one compare; no search loop, no loads of xp[0] / xp[n-1]
+  int b = (int)((x - f.g_x0) * f.g_inv);                  // NaN -> 0
+  b = max(0, min(b, f.g_n - 1));
+  const unsigned g = (unsigned)reinterpret_cast<const int32_t*>(tab + f.g_off)[b];
+  int j = (int)(g & SS_GUIDE_INDEX);
+  if (g & SS_GUIDE_MANY) {
+    while (j > 0 && xp[j] > x) --j;
+    while (j + 1 < n && xp[j + 1] <= x) ++j;
+  } else {
+    j += ((g & SS_GUIDE_ONE) && x >= xp[min(j + 1, n - 1)]) ? 1 : 0;
+  }
+  return j;
+}
+
+// value at an already located interval; the range and NaN cases are selects against the
+// table ends kept in the descriptor (p[2], p[3])
+__device__ __forceinline__ double lin_value(const SSFunc& f, const double* __restrict__ tab, int j,
+                                            double x, double fill_lo, double fill_hi) {
+  const double* __restrict__ xp = tab + f.x_off;
+  const double* __restrict__ fp = tab + f.c_off;
+  const int n = f.n;
+  const double xj = xp[j], fj = fp[j];
+  double r = (j == n - 1 || xj == x) ? fj : __dadd_rn(__dmul_rn(fp[n + j], __dsub_rn(x, xj)), fj);
+  r = (x < f.p[2]) ? fill_lo : r;
+  r = (x > f.p[3]) ? fill_hi : r;
+  return (x != x) ? x : r;
+}
+
 __device__ __forceinline__ double lin_eval(const SSFunc& f, const double* __restrict__ tab,
                                            double x, double fill_lo, double fill_hi) {
   const double* __restrict__ xp = tab + f.x_off;
   const double* __restrict__ fp = tab + f.c_off;
   const int n = f.n;
-  if (f.g_n > 0) {
-    // guided table (the survey curves): bucket -> knot with at most one compare, the range
-    // and NaN cases as selects against the table ends kept in the descriptor (p[2], p[3]);
-    // no search loop, no loads of xp[0] / xp[n-1]
-    int b = (int)((x - f.g_x0) * f.g_inv);                  // NaN -> 0
-    b = max(0, min(b, f.g_n - 1));
-    const unsigned g = (unsigned)reinterpret_cast<const int32_t*>(tab + f.g_off)[b];
-    int j = (int)(g & SS_GUIDE_INDEX);
-    if (g & SS_GUIDE_MANY) {
-      while (j > 0 && xp[j] > x) --j;
-      while (j + 1 < n && xp[j + 1] <= x) ++j;
-    } else {
-      j += ((g & SS_GUIDE_ONE) && x >= xp[min(j + 1, n - 1)]) ? 1 : 0;
-    }
-    const double xj = xp[j], fj = fp[j];
-    double r = (j == n - 1 || xj == x) ? fj : __dadd_rn(__dmul_rn(fp[n + j], __dsub_rn(x, xj)), fj);
-    r = (x < f.p[2]) ? fill_lo : r;
-    r = (x > f.p[3]) ? fill_hi : r;
-    return (x != x) ? x : r;
-  }
+  if (f.g_n > 0) return lin_value(f, tab, lin_locate(f, tab, x), x, fill_lo, fill_hi);
   if (x != x) return x;
   if (x < xp[0]) return fill_lo;
   if (x > xp[n - 1]) return fill_hi;
@@ -395,6 +431,21 @@ __device__ __forceinline__ HpLoc hp_locate(double lon_deg, double lat_deg) {
     if (tt == 4.0) tt = 0.0;
   }
   L.tt = tt;
+  return L;
+}
+
+// The fused path: z = cos(colatitude) = w_z and tt = longitude / (pi/2) straight from the
+// rotated unit vector (the reference goes through degrees and back; equal to ~1e-16).  The
+// callers keep the reference's own chain within 0.8 deg of a pole.
+__device__ __forceinline__ HpLoc hp_from_vector(double wz, double lon_rad) {
+  HpLoc L;
+  L.z = wz;
+  const double v = __dmul_rn(lon_rad, kNum[9]);
+  L.tt = (v < 0.0) ? v + 4.0 : v;
+  if (L.tt >= 4.0) L.tt = 0.0;
+  L.sth = 0.0;
+  L.have_sth = false;
+  L.valid = true;
   return L;
 }
 
@@ -482,7 +533,7 @@ __device__ __forceinline__ double photo_error_log(const SSParams& p, const doubl
   bright = mag < sat;
   if (bright) return 0.0;
   return (delta <= p.delta_saturation && mag >= sat) ? p.log_err_at_dsat
-                                                     : lin_eval(p.photo_error, tab, delta, 1.0, 1.0);
+                                                     : lin_eval(p.photo_error, tab, delta, p.photo_error.p[0], p.photo_error.p[0]);
 }
 
 // statistical (+) systematic error in quadrature (reference surveys.py:288-290)
@@ -509,7 +560,224 @@ __device__ __forceinline__ double efficiency(const SSParams& p, const SSFunc& f,
   if (mag < sat) return 0.0;
   const double delta = __dsub_rn(mag, maglim);
   if (mag > sat && delta <= p.delta_saturation) return 1.0;
-  return lin_eval(f, tab, delta, 0.0, 0.0);
+  return lin_eval(f, tab, delta, f.p[0], f.p[0]);
+}
+
+// the same two getters at an already located table interval, branch-free (the fused
+// observe step; guided tables only -- validate() insists on a guide for the survey curves)
+__device__ __forceinline__ double photo_error_log_at(const SSParams& p, const double* __restrict__ tab,
+                                                     double sat, double mag, double delta, int j,
+                                                     bool& bright) {
+  bright = mag < sat;
+  const double v = lin_value(p.photo_error, tab, j, delta, p.photo_error.p[0], p.photo_error.p[0]);
+  const double w = (delta <= p.delta_saturation && mag >= sat) ? p.log_err_at_dsat : v;
+  return bright ? 0.0 : w;
+}
+
+__device__ __forceinline__ double efficiency_at(const SSParams& p, const SSFunc& f,
+                                                const double* __restrict__ tab, double sat,
+                                                double mag, double maglim, double delta, int j) {
+  double r = lin_value(f, tab, j, delta, f.p[0], f.p[0]);
+  r = (mag > sat && delta <= p.delta_saturation) ? 1.0 : r;
+  r = (mag < sat) ? 0.0 : r;
+  return (maglim < sat || maglim != maglim) ? 0.0 : r;
+}
+
+// ---------------------------------------------------------------- per-star observe arithmetic
+// Everything of StreamInjector.inject's per-star body that follows the map gathers
+// (reference observed.py:163-291), shared by the generic kernel and the production
+// kernel so that both produce the same bytes.
+struct ObsOut {
+  double mobs[2], err[2];
+  bool observed, perfect, unseen, bad[2];
+};
+
+// sample_measured_magnitudes in the short form
+//   F = 3631*10^(-0.4 m), F_obs = F + (F*err/1.0857362)*z, m_obs = -2.5 log10(F_obs/3631)
+//   <=>  F_obs > 0 <=> t > 0,  m_obs = m - 2.5 log10(t),  t = 1 + (err/1.0857362)*z
+// (one log10 instead of exp10 + log10 + two divisions; equal to rounding while the flux
+// neither under- nor overflows), all in double.  A bad magnitude (F_obs <= 0 or NaN: the
+// reference's "BAD_MAG") is returned as NaN -- a good one is never NaN.
+__device__ __forceinline__ void noisy_mag_f64(const SSParams& p, int b, double mt, double loge,
+                                              bool bright, double z, double& err, double& mobs) {
+  const double stat = bright ? p.err_bright : exp10_nb(loge);
+  const double sys = p.sys_error[b];                                // surveys.py:288-290
+  err = sqrt_nb(__dadd_rn(__dmul_rn(stat, stat), __dmul_rn(sys, sys)));
+  const double t = 1.0 + err * kNum[11] * z;
+  mobs = (t > 0.0) ? mt - 2.5 * log10_nb(t) : nan_d();
+}
+
+// exact flux-space noise for magnitudes whose flux under-/overflows the short form, or
+// log-errors outside exp10_nb's domain (observed.py:863-904, :984-1035); rare, out of line.
+// Returns (err, mobs).
+__device__ SS_COLD double2 noisy_mag_exact(const SSParams& p, int b, double mt, double loge,
+                                                bool bright, double z) {
+  const double err = photo_error_total(p, b, loge, bright);
+  double mobs = nan_d();
+  if (fabs(mt) < 200.0) {
+    const double t = 1.0 + err * kNum[11] * z;
+    if (t > 0.0) mobs = mt - 2.5 * log10(t);
+  } else {
+    const double flux = __dmul_rn(3631.0, exp10(__dmul_rn(-0.4, mt)));
+    const double sig = __ddiv_rn(__dmul_rn(flux, err), 1.0857362);
+    const double fobs = __dadd_rn(flux, __dmul_rn(sig, z));
+    if (fobs > 0.0) mobs = __dmul_rn(-2.5, log10(__ddiv_rn(fobs, 3631.0)));
+  }
+  return make_double2(err, mobs);
+}
+
+// the double short form, out of line: SS_MATH_FAST's redo inside its guard band
+__device__ SS_COLD double2 noisy_mag_redo(const SSParams& p, int b, double mt, double loge,
+                                               bool bright, double z) {
+  double err, mobs;
+  noisy_mag_f64(p, b, mt, loge, bright, z, err, mobs);
+  return make_double2(err, mobs);
+}
+
+// share: bit 0 = the completeness curve sits on the photo-error curve's abscissae, bit 1 = so
+// does the detection-only curve (same blob offsets: BlobPacker de-duplicates): located once
+__device__ __forceinline__ int curve_share(const SSParams& p) {
+  const SSFunc& e = p.photo_error;
+  const SSFunc& c = p.completeness;
+  const SSFunc& d = p.detection;
+  const int sc = (c.n == e.n && c.x_off == e.x_off && c.g_n == e.g_n && c.g_off == e.g_off) ? 1 : 0;
+  const int sd = (d.n == e.n && d.x_off == e.x_off && d.g_n == e.g_n && d.g_off == e.g_off) ? 2 : 0;
+  return sc | sd;
+}
+
+template <int MATH>
+__device__ __forceinline__ void observe_star(const SSParams& p, const double* __restrict__ tab,
+                                             int share, bool band_g, bool band_r, double mag_g,
+                                             double mag_r, double ebv, double ml_g, double ml_r,
+                                             double z_g, double z_r, double u_det, double u_det2,
+                                             ObsOut& o) {
+  // Stage 1: per band, the table look-ups.  Stage 2: the error / noise arithmetic of BOTH
+  // bands as one straight-line block, so that the two dependency chains interleave.
+  double ext2[2], mt2[2], loge2[2], zf2[2], dl2[2], ml2[2];
+  int j2[2];
+  bool bright2[2], have2[2], good2[2];
+  bool plain = true;
+#pragma unroll
+  for (int b = 0; b < 2; ++b) {
+    have2[b] = (b == SS_BAND_G) ? band_g : band_r;
+    const double mag = b == SS_BAND_G ? mag_g : mag_r;
+    ml2[b] = b == SS_BAND_G ? ml_g : ml_r;
+    zf2[b] = b == SS_BAND_G ? z_g : z_r;
+    ext2[b] = __dmul_rn(p.coeff_extinc[b], ebv);                   // surveys.py:228
+    mt2[b] = __dadd_rn(mag, ext2[b]);                              // observed.py:167
+    dl2[b] = __dsub_rn(mt2[b], ml2[b]);
+    bright2[b] = false;
+    good2[b] = false;
+    loge2[b] = nan_d();
+    j2[b] = 0;
+    o.err[b] = o.mobs[b] = nan_d();
+    if (!have2[b]) continue;
+    j2[b] = lin_locate(p.photo_error, tab, dl2[b]);
+    loge2[b] = photo_error_log_at(p, tab, p.saturation[b], mt2[b], dl2[b], j2[b], bright2[b]);  // surveys.py:234-286
+    plain = plain && fabs(mt2[b]) < 200.0 && !(fabs(loge2[b]) >= 300.0);
+  }
+  // completeness / detection Bernoulli trials in the survey's completeness band (observed.py:224-243)
+  const bool cr = p.completeness_band == SS_BAND_R;
+  const double mt_c = cr ? mt2[1] : mt2[0], ml_c = cr ? ml2[1] : ml2[0], dl_c = cr ? dl2[1] : dl2[0];
+  const double sat_c = cr ? p.saturation[1] : p.saturation[0];
+  const int j_p = cr ? j2[1] : j2[0];
+  const int j_c = (share & 1) ? j_p : lin_locate(p.completeness, tab, dl_c);
+  const bool flag_c = u_det <= efficiency_at(p, p.completeness, tab, sat_c, mt_c, ml_c, dl_c, j_c);
+  bool flag_d = false;
+  if (p.perfect_galstarsep) {
+    const int j_d = (share & 2) ? j_p : lin_locate(p.detection, tab, dl_c);
+    flag_d = u_det2 <= efficiency_at(p, p.detection, tab, sat_c, mt_c, ml_c, dl_c, j_d);
+  }
+  o.unseen = ml_c != ml_c;
+  if (plain) {
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      if (MATH == SS_MATH_FAST) {
+        // fp32 values on the MUFU units.  stat carries ~1e-6 relative error, so does
+        // x = err*z/1.0857362; the log amplifies the error of t = 1 + x by 1/t: inside the
+        // guard band the star is redone in double (it also owns the sign decision there).
+        const float lf = (float)loge2[b];
+        const float stat = bright2[b] ? (float)p.err_bright : exp2f(lf * 3.3219281f);
+        const float sys = (float)p.sys_error[b];
+        const float ef = sqrtf(fmaf(stat, stat, sys * sys));
+        const float x = ef * 0.92103404f * (float)zf2[b];
+        const float t = 1.0f + x;
+        if (fabsf(t) < 0.012f * (1.0f + fabsf(x)) || fabsf(lf) >= 30.0f) {   // NaN: not taken
+          const double2 r = noisy_mag_redo(p, b, mt2[b], loge2[b], bright2[b], zf2[b]);
+          o.err[b] = r.x;
+          o.mobs[b] = r.y;
+        } else {
+          o.err[b] = (double)ef;
+          o.mobs[b] = (t > 0.0f) ? mt2[b] - (double)(0.75257499f * __log2f(t)) : nan_d();
+        }
+      } else {
+        noisy_mag_f64(p, b, mt2[b], loge2[b], bright2[b], zf2[b], o.err[b], o.mobs[b]);
+      }
+      good2[b] = o.mobs[b] == o.mobs[b];
+    }
+  } else {
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+      if (have2[b]) {
+        const double2 r = noisy_mag_exact(p, b, mt2[b], loge2[b], bright2[b], zf2[b]);
+        o.err[b] = r.x;
+        o.mobs[b] = r.y;
+        good2[b] = r.y == r.y;
+      }
+  }
+  bool valid = true, snr_ok = true, snr_r_ok = true;
+#pragma unroll
+  for (int b = 0; b < 2; ++b) {
+    o.bad[b] = false;
+    if (!have2[b]) {
+      o.err[b] = o.mobs[b] = nan_d();
+      continue;
+    }
+    if (good2[b] && p.dust_correction) o.mobs[b] = __dsub_rn(o.mobs[b], ext2[b]);  // observed.py:194-208
+    valid = valid && good2[b];
+    o.bad[b] = !good2[b];
+    // 1/magerr >= 5 (observed.py:266-281) decided on the monotone pre-image log10(err_stat)
+    const bool ok = bright2[b] ? (p.snr_bright_ok[b] != 0) : (loge2[b] <= p.snr_loge_max[b]);
+    if (p.snr_cut[b]) snr_ok = snr_ok && ok;
+    if (b == SS_BAND_R) snr_r_ok = ok;                             // observed.py:283-286
+  }
+  o.observed = valid && flag_c && snr_ok;
+  o.perfect = p.perfect_galstarsep && valid && flag_d && snr_ok && snr_r_ok;
+}
+
+// histogram bin in fp32 (SSParams.hist_*): t = ((float)v - lo) * inv, two roundings; -1 when
+// outside or NaN
+__device__ __forceinline__ int hist_bin(float v, float lo, float inv) {
+  const float t = __fmul_rn(__fsub_rn(v, lo), inv);
+  return (t >= 0.0f && t < (float)SS_HIST_BINS) ? (int)t : -1;
+}
+
+// ---------------------------------------------------------------- HEALPix, 32-bit variant
+// ang2pix RING from (z, tt) for nside <= 8192 (npix < 2^31): the same floating-point
+// expressions as hp_ring, integer part in 32 bits.
+__device__ __forceinline__ int hp_ring32(double z, double tt, int nside) {
+  const double ns = (double)nside;
+  const double za = fabs(z);
+  if (za <= 2.0 / 3.0) {
+    const int nl4 = 4 * nside;
+    const double t1 = __dmul_rn(ns, __dadd_rn(0.5, tt));
+    const double t2 = __dmul_rn(__dmul_rn(ns, z), 0.75);
+    const int jp = __double2int_rz(__dsub_rn(t1, t2));
+    const int jm = __double2int_rz(__dadd_rn(t1, t2));
+    const int ir = nside + 1 + jp - jm;
+    const int kshift = 1 - (ir & 1);
+    const int t = jp + jm - nside + kshift + 1 + nl4 + nl4;
+    const int ip = ((nside & (nside - 1)) == 0 && nside > 1) ? ((t >> 1) & (nl4 - 1))
+                                                             : ((t >> 1) % nl4);
+    return 2 * nside * (nside - 1) + (ir - 1) * nl4 + ip;
+  }
+  const double tp = __dsub_rn(tt, (double)__double2int_rz(tt));
+  const double tmp = __dmul_rn(ns, sqrt(__dmul_rn(3.0, __dsub_rn(1.0, za))));
+  const int jp = __double2int_rz(__dmul_rn(tp, tmp));
+  const int jm = __double2int_rz(__dmul_rn(__dsub_rn(1.0, tp), tmp));
+  const int ir = jp + jm + 1;
+  const int ip = __double2int_rz(__dmul_rn(tt, (double)ir));
+  return (z > 0) ? 2 * ir * (ir - 1) + ip : 12 * nside * nside - 2 * ir * (ir + 1) + ip;
 }
 
 }  // namespace ss

@@ -21,6 +21,14 @@
 #ifndef SS_BLOCK
 #define SS_BLOCK 1024
 #endif
+// geometry of the production kernel k_fused: threads per CTA and resident CTAs per SM
+// (the register budget follows: 65536 / (block * ctas) per thread)
+#ifndef SS_FUSED_BLOCK
+#define SS_FUSED_BLOCK 1024
+#endif
+#ifndef SS_FUSED_MIN_CTAS
+#define SS_FUSED_MIN_CTAS 1
+#endif
 
 namespace {
 
@@ -147,17 +155,34 @@ struct GridRow {
   double sinx, cosx;  // sin/cos of radians(x)
 };
 
+// thresholds thr[lo .. lo+k-1] lie in one bucket of the u -> step table: guess the step by
+// position inside the bucket, then fix up (one or two trips)
+__device__ __forceinline__ int step_scan(const double* __restrict__ thr, int lo, int k, double u,
+                                         uint32_t lut_n) {
+  const double fb = u * (double)lut_n;
+  int j = lo + (int)((fb - (double)(int)fb) * (double)k);   // candidate: first idx with u < thr[idx]
+  const int hi = lo + k;
+  while (j > lo && u < __ldg(&thr[j - 1])) --j;
+  while (j < hi && u >= __ldg(&thr[j])) ++j;
+  return j;
+}
+
+__device__ __forceinline__ void load_grid_row(const double* __restrict__ grid_rows, long long idx,
+                                              GridRow& row) {
+  const double2* __restrict__ rows = reinterpret_cast<const double2*>(grid_rows) + 4 * idx;
+  const double2 r0 = __ldg(rows), r1 = __ldg(rows + 1), r2 = __ldg(rows + 2), r3 = __ldg(rows + 3);
+  row.thr = r0.x; row.x = r0.y; row.c = r1.x; row.s = r1.y;
+  row.dc = r2.x; row.ds = r2.y; row.sinx = r3.x; row.cosx = r3.y;
+}
+
 // inverse_transform_sample (reference samplers.py:55-76) as a direct lookup: the
 // sample index rint(interp(u)) is a step function of u, so the step a draw falls in is
 // the number of host-computed exact thresholds <= u, and each step has its own row (the
 // index may step down as well as up: non-monotone CDFs).  A uniform table over u gives
 // the step at the bucket's edges; the few thresholds inside the bucket settle it.
-template <bool PRE>
-__device__ __forceinline__ bool grid_sample(const KArgs& a, double u, GridRow& row,
-                                            double2 pre = make_double2(0.0, 0.0)) {
+__device__ __forceinline__ bool grid_sample(const KArgs& a, double u, GridRow& row) {
   const SSParams& p = a.p;
   long long idx;
-  const double2* __restrict__ rows = reinterpret_cast<const double2*>(a.t.grid_rows);
   if (u != u) return false;
   if (u < 0.0 || u > p.cdf_last) {
     idx = p.grid_nthr + 1;                    // interp1d fill_value = 0.0: the fill row
@@ -171,31 +196,16 @@ __device__ __forceinline__ bool grid_sample(const KArgs& a, double u, GridRow& r
   } else {
     // One 16-byte table entry per bucket of u: (first index lo, number k of thresholds
     // inside the bucket, thr[lo]).  For k <= 1 (82 % of the stars at 2^17 buckets) the
-    // index costs ONE round trip and no loop; otherwise a position-proportional guess
-    // keeps the warp-divergent fix-up loops to one or two trips.  (Measured: 2^17 buckets
-    // -- a 2 MB table that partly lives in L1 -- beat both 2^15 and 2^20.)
-    const double fb = u * (double)p.grid_lut_n;
-    const int b = (int)fb;
-    // PRE: the bucket entry was fetched at the end of the previous star's iteration
-    const double2 e = PRE ? pre : __ldg(&reinterpret_cast<const double2*>(a.t.grid_lut)[b]);
+    // index costs ONE round trip and no loop.  (Measured: 2^17 buckets -- a 2 MB table
+    // that partly lives in L1 -- beat both 2^15 and 2^20.)
+    const int b = (int)(u * (double)p.grid_lut_n);
+    const double2 e = __ldg(&reinterpret_cast<const double2*>(a.t.grid_lut)[b]);
     const long long packed = __double_as_longlong(e.x);
     const int lo = (int)(packed & 0xffffffffLL), k = (int)(packed >> 32);
-    if (k <= 1) {
-      idx = lo + ((k == 1 && u >= e.y) ? 1 : 0);
-    } else {
-      // thresholds thr[lo .. lo+k-1] lie in this bucket: guess by position, then fix up
-      const double* __restrict__ thr = a.t.grid_thr;
-      int j = lo + (int)((fb - (double)b) * (double)k);   // candidate: first idx with u < thr[idx]
-      const int hi = lo + k;
-      while (j > lo && u < __ldg(&thr[j - 1])) --j;
-      while (j < hi && u >= __ldg(&thr[j])) ++j;
-      idx = j;
-    }
+    idx = (k <= 1) ? lo + ((k == 1 && u >= e.y) ? 1 : 0)
+                   : step_scan(a.t.grid_thr, lo, k, u, (uint32_t)p.grid_lut_n);
   }
-  const double2 r0 = __ldg(&rows[4 * (size_t)idx]), r1 = __ldg(&rows[4 * (size_t)idx + 1]);
-  const double2 r2 = __ldg(&rows[4 * (size_t)idx + 2]), r3 = __ldg(&rows[4 * (size_t)idx + 3]);
-  row.thr = r0.x; row.x = r0.y; row.c = r1.x; row.s = r1.y;
-  row.dc = r2.x; row.ds = r2.y; row.sinx = r3.x; row.cosx = r3.y;
+  load_grid_row(a.t.grid_rows, idx, row);
   return true;
 }
 
@@ -239,10 +249,17 @@ __device__ __forceinline__ double invcdf_phi1(const KArgs& a, const int32_t* __r
 // arithmetic) and the device finds the segment with the same one-round-trip bucket table
 // as the phi1 grid: no search loops in shared memory, no division, 100 KB less shared
 // memory.  Rows: (U_k, g_k, dg/du, r_k, dr/du, 0); thr[k] = U_{k+1}.
-template <bool PRE>
+__device__ __forceinline__ void iso_row_eval(const double* __restrict__ iso_rows, long long idx,
+                                             double u, double& m1, double& m2) {
+  const double2* __restrict__ rows = reinterpret_cast<const double2*>(iso_rows) + 3 * idx;
+  const double2 r0 = __ldg(rows), r1 = __ldg(rows + 1), r2 = __ldg(rows + 2);
+  const double du = u - r0.x;
+  m1 = r0.y + r1.x * du;
+  m2 = r1.y + r2.x * du;
+}
+
 __device__ __forceinline__ void iso_sample_direct(const KArgs& a, double u, double& m1, double& m2,
-                                                  unsigned& domain_err,
-                                                  double2 pre = make_double2(0.0, 0.0)) {
+                                                  unsigned& domain_err) {
   const SSParams& p = a.p;
   if (!(u >= 0.0 && u <= 1.0)) {             // interp1d(bounds_error=True) raises
     domain_err++;
@@ -253,27 +270,34 @@ __device__ __forceinline__ void iso_sample_direct(const KArgs& a, double u, doub
   if (u >= 1.0) {
     idx = p.iso_n - 1;
   } else {
-    const double fb = u * (double)p.iso_lut_n;
-    const int b = (int)fb;
-    const double2 e = PRE ? pre : __ldg(&reinterpret_cast<const double2*>(a.t.iso_lut)[b]);
+    const int b = (int)(u * (double)p.iso_lut_n);
+    const double2 e = __ldg(&reinterpret_cast<const double2*>(a.t.iso_lut)[b]);
     const long long packed = __double_as_longlong(e.x);
     const int lo = (int)(packed & 0xffffffffLL), k = (int)(packed >> 32);
-    if (k <= 1) {
-      idx = lo + ((k == 1 && u >= e.y) ? 1 : 0);
-    } else {
-      const double* __restrict__ thr = a.t.iso_thr;
-      int j = lo + (int)((fb - (double)b) * (double)k);
-      const int hi = lo + k;
-      while (j > lo && u < __ldg(&thr[j - 1])) --j;
-      while (j < hi && u >= __ldg(&thr[j])) ++j;
-      idx = j;
-    }
+    idx = (k <= 1) ? lo + ((k == 1 && u >= e.y) ? 1 : 0)
+                   : step_scan(a.t.iso_thr, lo, k, u, (uint32_t)p.iso_lut_n);
   }
-  const double2* __restrict__ rows = reinterpret_cast<const double2*>(a.t.iso_rows);
-  const double2 r0 = __ldg(&rows[3 * idx]), r1 = __ldg(&rows[3 * idx + 1]), r2 = __ldg(&rows[3 * idx + 2]);
-  const double du = u - r0.x;
-  m1 = r0.y + r1.x * du;
-  m2 = r1.y + r2.x * du;
+  iso_row_eval(a.t.iso_rows, idx, u, m1, m2);
+}
+
+// stream frame -> ICRS (reference observed.py:478-575; astropy: lon = atan2(y, x),
+// lat = atan2(z, hypot(x, y))).  sl, cl = sin / cos of phi1; the transverse angle phi2 is
+// small (Taylor series).  |w| = 1, so the branch-free atan2 / sqrt are inside their domains
+// and the two chains interleave.
+__device__ __forceinline__ void rotate_star(const SSParams& p, double sl, double cl, double phi2,
+                                            double& wx, double& wy, double& wz, double& lon,
+                                            double& ra, double& dec) {
+  double sb, cb;
+  ss::sincos_small(phi2 * ss::kNum[8], sb, cb);
+  const double v0 = cb * cl, v1 = cb * sl, v2 = sb;
+  wx = p.R[0] * v0 + p.R[3] * v1 + p.R[6] * v2;
+  wy = p.R[1] * v0 + p.R[4] * v1 + p.R[7] * v2;
+  wz = p.R[2] * v0 + p.R[5] * v1 + p.R[8] * v2;
+  const double R2D = ss::kNum[7];
+  lon = ss::atan2_nb(wy, wx);
+  dec = ss::atan2_nb(wz, ss::sqrt_nb(wx * wx + wy * wy)) * R2D;
+  ra = lon * R2D;
+  ra = (ra < 0.0) ? ra + 360.0 : ra;
 }
 
 // ugali imf.sample + isochrone interp1d (reference model.py:590-602)
@@ -332,17 +356,17 @@ __device__ __forceinline__ void iso_sample(const SSParams& p, const double* __re
   m2 = ss::lin_at(mi, tab + p.iso_mag_off[1], ni, k, mass);
 }
 
-// ---------------------------------------------------------------- the star kernel
-// LEAN = the fused free-running production case, fixed at compile time: no injected
-// draws, no catalog inputs, grid-table density, both bands, RING maps.  It removes the
-// generic branches (and their code) from the hot loop; the launcher selects it.
-// MATH = SS_MATH_F64: every operation in double (parity grade, 1e-9 of the oracle).
-// MATH = SS_MATH_MIXED: Box-Muller, 10^x, the quadrature sum and the flux-noise log run
-// in fp32 on the MUFU units; any star whose photometric error or noisy flux lands within
-// a guard band of a decision threshold (SNR cut, flux > 0) is recomputed in double, so
-// pixel indices and flags stay bit-identical to the fp64 path while magnitudes agree to
-// ~1e-6 relative (the north star asks 1e-5).
-template <uint32_t ST, typename OutT, bool LEAN, int MATH>
+// ---------------------------------------------------------------- the star kernels
+// Random draws (include/streamsim_b200.h): two Philox blocks per star.
+//   POS: w0 -> u_phi1, w1 -> u_mass, (w2, w3) -> z_phi2, z_dist (or two uniforms)
+//   OBS: (w0, w1) -> z_r, z_g, w2 -> u_det, w3 -> u_det2
+//
+// k_stars: the generic kernel -- any stage mask, injected draws, partially filled
+// catalogs, every density kind, NESTED maps, draw export.
+// MATH = SS_MATH_F64: every value in double.  MATH = SS_MATH_FAST: identical decisions
+// (pixels, flags, counters), magerr / mag_obs VALUES from fp32 MUFU arithmetic with a
+// per-star double redo inside a guard band (ss::observe_star).
+template <uint32_t ST, typename OutT, int MATH>
 __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ KArgs a) {
   extern __shared__ __align__(16) unsigned char smem_blob[];
   __shared__ unsigned long long s_bar;
@@ -350,27 +374,27 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
   __shared__ unsigned int s_hist[SS_N_HIST * SS_HIST_BINS];
 
   const SSParams& p = a.p;
-  // launch-constant switches; compile-time constants in the LEAN instantiation
-  const double* const d_u_phi1 = LEAN ? nullptr : a.d.u_phi1;
-  const double* const d_u_mass = LEAN ? nullptr : a.d.u_mass;
-  const double* const d_n_phi2 = LEAN ? nullptr : a.d.n_phi2;
-  const double* const d_n_dist = LEAN ? nullptr : a.d.n_dist;
-  const double* const d_z_g = LEAN ? nullptr : a.d.z_flux[SS_BAND_G];
-  const double* const d_z_r = LEAN ? nullptr : a.d.z_flux[SS_BAND_R];
-  const double* const d_u_det = LEAN ? nullptr : a.d.u_det;
-  const double* const d_u_det2 = LEAN ? nullptr : a.d.u_det2;
-  const double* const in_phi1 = LEAN ? nullptr : a.in.phi1;
-  const double* const in_phi2 = LEAN ? nullptr : a.in.phi2;
-  const double* const in_dist = LEAN ? nullptr : a.in.dist;
-  double* const draws_out = LEAN ? nullptr : a.o.draws_out;
-  const int density_kind = LEAN ? SS_DENSITY_GRID : p.density_kind;
-  const bool has_dist = LEAN ? true : (p.has_dist != 0);
-  const bool has_iso = LEAN ? true : (p.has_iso != 0);
-  const bool band_g = LEAN ? true : (p.band_present[SS_BAND_G] != 0);
-  const bool band_r = LEAN ? true : (p.band_present[SS_BAND_R] != 0);
-  const int nest = LEAN ? 0 : p.nest;
+  const double* const d_u_phi1 = a.d.u_phi1;
+  const double* const d_u_mass = a.d.u_mass;
+  const double* const d_n_phi2 = a.d.n_phi2;
+  const double* const d_n_dist = a.d.n_dist;
+  const double* const d_z_g = a.d.z_flux[SS_BAND_G];
+  const double* const d_z_r = a.d.z_flux[SS_BAND_R];
+  const double* const d_u_det = a.d.u_det;
+  const double* const d_u_det2 = a.d.u_det2;
+  const double* const in_phi1 = a.in.phi1;
+  const double* const in_phi2 = a.in.phi2;
+  const double* const in_dist = a.in.dist;
+  double* const draws_out = a.o.draws_out;
+  const int density_kind = p.density_kind;
+  const bool has_dist = p.has_dist != 0;
+  const bool has_iso = p.has_iso != 0;
+  const bool band_g = p.band_present[SS_BAND_G] != 0;
+  const bool band_r = p.band_present[SS_BAND_R] != 0;
+  const int nest = p.nest;
   const bool want_cnt = a.o.counters != nullptr;
   const bool want_hist = want_cnt && p.hist_enable;
+  const int share = ss::curve_share(p);
 
   for (int i = threadIdx.x; i < SS_N_COUNTERS; i += blockDim.x) s_cnt[i] = 0;
   if (want_hist)
@@ -381,8 +405,8 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
   // guide) -- the same shared copy, or, when the phi1 grid table makes them cold, the
   // global blob (shared memory not spent on them is L1 cache for the gathers).
   const double* tab;
-  if (LEAN || a.blob_in_smem) {   // LEAN is only launched with the hot tables in shared memory:
-    stage_blob(smem_blob, a.t.blob, a.blob_bytes, &s_bar);   // its table reads compile to LDS
+  if (a.blob_in_smem) {
+    stage_blob(smem_blob, a.t.blob, a.blob_bytes, &s_bar);
     tab = reinterpret_cast<const double*>(smem_blob);
   } else {
     tab = reinterpret_cast<const double*>(a.t.blob);
@@ -394,29 +418,11 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
   __syncthreads();
 
   // Summary counters go straight to shared memory (uniform-address atomicAdd: REDUX +
-  // one ATOMS per warp) instead of living in eight registers across the whole loop body:
-  // registers, not instructions, are this kernel's scarce resource.
+  // one ATOMS per warp) instead of living in registers across the whole loop body.
 #define SS_COUNT(slot, cond) \
   do { if (want_cnt) atomicAdd(&s_cnt[slot], (cond) ? 1u : 0u); } while (0)
 
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  // LEAN software-pipelines the first look-ups: the position uniforms of the NEXT star and
-  // its two bucket entries (phi1 table, isochrone table) are fetched at the end of an
-  // iteration, where few registers are live, so that their L2 round trip is over when the
-  // next iteration starts.
-  double nx_u1 = 0.0, nx_u2 = 0.0;
-  double2 nx_eg = make_double2(0.0, 0.0), nx_ei = make_double2(0.0, 0.0);
-  auto prepare = [&](unsigned long long star) {
-    const uint4 w = ss::philox_block(a.offset + star, SS_DRAW_BLOCK_POS, a.seed);
-    nx_u1 = ss::u52(w.x, w.y);
-    nx_u2 = ss::u52(w.z, w.w);
-    nx_eg = __ldg(&reinterpret_cast<const double2*>(a.t.grid_lut)[(int)(nx_u1 * (double)p.grid_lut_n)]);
-    nx_ei = __ldg(&reinterpret_cast<const double2*>(a.t.iso_lut)[(int)(nx_u2 * (double)p.iso_lut_n)]);
-  };
-  if (LEAN) {
-    const unsigned long long first = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (first < a.n) prepare(first);
-  }
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n;
        i += stride) {
     const unsigned long long gi = a.offset + i;
@@ -429,56 +435,37 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
 
     // ------------------------------------------------ generate (model.py:106-157)
     if (ST & SS_STAGE_GENERATE) {
-      double u_phi1, u_mass;
-      if (LEAN) {
-        u_phi1 = nx_u1;
-        u_mass = nx_u2;
-      } else if (d_u_phi1 && (d_u_mass || !has_iso)) {
-        u_phi1 = d_u_phi1[i];
-        u_mass = has_iso ? d_u_mass[i] : 0.0;
-      } else {
-        const uint4 w = ss::philox_block(gi, SS_DRAW_BLOCK_POS, a.seed);
-        u_phi1 = ss::u52(w.x, w.y);
-        u_mass = ss::u52(w.z, w.w);
-        if (d_u_phi1) u_phi1 = d_u_phi1[i];
-        if (d_u_mass) u_mass = d_u_mass[i];
-      }
+      const bool z_track = p.track_sampler == SS_SAMPLER_GAUSSIAN;
+      const bool z_dist = p.dist_sampler == SS_SAMPLER_GAUSSIAN;
+      const bool all_given = d_u_phi1 && (d_u_mass || !has_iso) && d_n_phi2 && (d_n_dist || !has_dist);
+      uint4 w = make_uint4(0u, 0u, 0u, 0u);
+      if (!all_given) w = ss::philox_block(gi, SS_DRAW_BLOCK_POS, a.seed);
+      double u_phi1 = d_u_phi1 ? d_u_phi1[i] : ss::u32(w.x);
+      const double u_mass = d_u_mass ? d_u_mass[i] : ss::u32(w.y);
+      double z0 = 0, z1 = 0;
+      if (!all_given && (z_track || (has_dist && z_dist))) ss::bm32(w.z, w.w, z0, z1);
+      const double n_phi2 = d_n_phi2 ? d_n_phi2[i] : (z_track ? z0 : ss::u32(w.z));
+      const double n_dist = d_n_dist ? d_n_dist[i] : (z_dist ? z1 : ss::u32(w.w));
+
       const double phi1_given = in_phi1 ? in_phi1[i] : ss::nan_d();
       if (phi1_given == phi1_given) {
         phi1 = phi1_given;
       } else if (density_kind == SS_DENSITY_GRID) {
-        on_grid = LEAN ? grid_sample<true>(a, u_phi1, row, nx_eg) : grid_sample<false>(a, u_phi1, row);
+        on_grid = grid_sample(a, u_phi1, row);
         phi1 = on_grid ? row.x : ss::nan_d();
       } else if (density_kind == SS_DENSITY_UNIFORM) {
         phi1 = __dadd_rn(__dmul_rn(u_phi1, __dsub_rn(p.density_hi, p.density_lo)), p.density_lo);
       } else if (density_kind == SS_DENSITY_INVCDF) {
         phi1 = invcdf_phi1(a, sitab, u_phi1);
-      } else if (density_kind == SS_DENSITY_GAUSSIAN) {  // u_phi1 slot carries a normal draw
-        double z = u_phi1;
+      } else if (density_kind == SS_DENSITY_GAUSSIAN) {  // the u_phi1 slot carries a normal draw
         if (!d_u_phi1) {
-          double z1;
-          const uint4 w = ss::philox_block(gi, SS_DRAW_BLOCK_DENSITY_Z, a.seed);
-          ss::bm32(w.x, w.y, z, z1);
+          double zz;
+          const uint4 wz4 = ss::philox_block(gi, SS_DRAW_BLOCK_DENSITY_Z, a.seed);
+          ss::bm32(wz4.x, wz4.y, u_phi1, zz);
         }
-        phi1 = __dadd_rn(__dmul_rn(z, p.density_hi), p.density_lo);
+        phi1 = __dadd_rn(__dmul_rn(u_phi1, p.density_hi), p.density_lo);
       } else {
         phi1 = ss::nan_d();
-      }
-
-      double n_phi2, n_dist;
-      if (d_n_phi2 && (d_n_dist || !has_dist)) {
-        n_phi2 = d_n_phi2[i];
-        n_dist = has_dist ? d_n_dist[i] : 0.0;
-      } else {
-        const uint4 wn = ss::philox_block(gi, SS_DRAW_BLOCK_NORMAL, a.seed);
-        const bool need_z = (p.track_sampler == SS_SAMPLER_GAUSSIAN) ||
-                            (has_dist && p.dist_sampler == SS_SAMPLER_GAUSSIAN);
-        double z0 = 0, z1 = 0;
-        if (need_z) ss::bm32(wn.x, wn.y, z0, z1);
-        n_phi2 = (p.track_sampler == SS_SAMPLER_GAUSSIAN) ? z0 : ss::u32(wn.x);
-        n_dist = (p.dist_sampler == SS_SAMPLER_GAUSSIAN) ? z1 : ss::u32(wn.y);
-        if (d_n_phi2) n_phi2 = d_n_phi2[i];
-        if (d_n_dist) n_dist = d_n_dist[i];
       }
       if (draws_out) {
         draws_out[SS_DRAW_U_PHI1 * a.n + i] = u_phi1;
@@ -491,7 +478,7 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
         phi2 = phi2_given;
       } else {
         double c = row.c, s = row.s;
-        if (!LEAN && !on_grid) track_eval(p.track_center, p.track_spread, stab, phi1, c, s);
+        if (!on_grid) track_eval(p.track_center, p.track_spread, stab, phi1, c, s);
         phi2 = track_draw(c, s, p.track_sampler, n_phi2, c_dom);
       }
       const double dist_given = in_dist ? in_dist[i] : ss::nan_d();
@@ -499,13 +486,12 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
       if (has_dist || has_iso) {
         if (!(dist_given == dist_given) && has_dist) {
           double c = row.dc, s = row.ds;
-          if (!LEAN && !on_grid) track_eval(p.dist_center, p.dist_spread, stab, phi1, c, s);
+          if (!on_grid) track_eval(p.dist_center, p.dist_spread, stab, phi1, c, s);
           dist = track_draw(c, s, p.dist_sampler, n_dist, c_dom);
         }
         if (has_iso) {
           double m1, m2;
-          if (LEAN) iso_sample_direct<true>(a, u_mass, m1, m2, c_dom, nx_ei);
-          else if (p.iso_direct) iso_sample_direct<false>(a, u_mass, m1, m2, c_dom);
+          if (p.iso_direct) iso_sample_direct(a, u_mass, m1, m2, c_dom);
           else iso_sample(p, tab, itab, u_mass, m1, m2, c_dom);
           mag_g = __dadd_rn(m1, dist);
           mag_r = __dadd_rn(m2, dist);
@@ -525,20 +511,9 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
         phi1 = in_phi1[i];
         phi2 = in_phi2[i];
       }
-      double sl = row.sinx, cl = row.cosx, sb, cb;
-      if (!LEAN && !on_grid) sincospi(phi1 * (1.0 / 180.0), &sl, &cl);
-      ss::sincos_small(phi2 * ss::kNum[8], sb, cb);
-      const double v0 = cb * cl, v1 = cb * sl, v2 = sb;
-      wx = p.R[0] * v0 + p.R[3] * v1 + p.R[6] * v2;
-      wy = p.R[1] * v0 + p.R[4] * v1 + p.R[7] * v2;
-      wz = p.R[2] * v0 + p.R[5] * v1 + p.R[8] * v2;
-      const double R2D = ss::kNum[7];
-      // astropy: lon = atan2(y, x), lat = atan2(z, hypot(x, y)).  |w| = 1, so the branch-
-      // free versions are inside their domains; the two chains interleave.
-      lon = ss::atan2_nb(wy, wx);
-      dec = ss::atan2_nb(wz, ss::sqrt_nb(wx * wx + wy * wy)) * R2D;
-      ra = lon * R2D;
-      ra = (ra < 0.0) ? ra + 360.0 : ra;
+      double sl = row.sinx, cl = row.cosx;
+      if (!on_grid) sincospi(phi1 * (1.0 / 180.0), &sl, &cl);
+      rotate_star(p, sl, cl, phi2, wx, wy, wz, lon, ra, dec);
       put<OutT>(a.o.ra, i, ra);
       put<OutT>(a.o.dec, i, dec);
     }
@@ -555,16 +530,7 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
       }
       ss::HpLoc L;
       if ((ST & SS_STAGE_ROTATE) && fabs(wz) < 0.9999 && lon == lon) {
-        // fused path: z = cos(colatitude) = w_z and tt = longitude/(pi/2) straight from
-        // the rotated unit vector (the reference goes through degrees and back; equal to
-        // ~1e-16).  Within 0.8 deg of a pole the reference's own chain is used.
-        L.z = wz;
-        const double v = __dmul_rn(lon, ss::kNum[9]);
-        L.tt = (v < 0.0) ? v + 4.0 : v;
-        if (L.tt >= 4.0) L.tt = 0.0;
-        L.sth = 0.0;
-        L.have_sth = false;
-        L.valid = true;
+        L = ss::hp_from_vector(wz, lon);
       } else {
         L = ss::hp_locate(ra, dec);
       }
@@ -592,203 +558,56 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
         if (a.o.pix) a.o.pix[i] = -1;
       }
 
-      double z_g, z_r;
-      if (d_z_g && d_z_r) {
-        z_g = d_z_g[i];
-        z_r = d_z_r[i];
-      } else {
-        // recomputed rather than kept live since the generate stage: registers are the
-        // scarce resource of this kernel (measured +9 % over carrying the words across)
-        const uint4 wn = ss::philox_block(gi, SS_DRAW_BLOCK_NORMAL, a.seed);
-        ss::bm32(wn.z, wn.w, z_r, z_g);
-        if (d_z_g) z_g = d_z_g[i];
-        if (d_z_r) z_r = d_z_r[i];
+      const bool need_d2 = p.perfect_galstarsep != 0;
+      const bool all_given = d_z_g && d_z_r && d_u_det && (d_u_det2 || !need_d2);
+      uint4 w = make_uint4(0u, 0u, 0u, 0u);
+      double z_r = 0, z_g = 0;
+      if (!all_given) {
+        w = ss::philox_block(gi, SS_DRAW_BLOCK_OBS, a.seed);
+        ss::bm32(w.x, w.y, z_r, z_g);
       }
-      double u_det, u_det2;
-      if (d_u_det && (d_u_det2 || !p.perfect_galstarsep)) {
-        u_det = d_u_det[i];
-        u_det2 = p.perfect_galstarsep ? d_u_det2[i] : 0.0;
-      } else {
-        const uint4 w = ss::philox_block(gi, SS_DRAW_BLOCK_DETECT, a.seed);
-        u_det = ss::u52(w.x, w.y);
-        u_det2 = ss::u52(w.z, w.w);
-        if (d_u_det) u_det = d_u_det[i];
-        if (d_u_det2) u_det2 = d_u_det2[i];
-      }
-
+      if (d_z_g) z_g = d_z_g[i];
+      if (d_z_r) z_r = d_z_r[i];
+      const double u_det = d_u_det ? d_u_det[i] : ss::u32(w.z);
+      const double u_det2 = d_u_det2 ? d_u_det2[i] : ss::u32(w.w);
       if (draws_out) {
         draws_out[SS_DRAW_Z_G * a.n + i] = z_g;
         draws_out[SS_DRAW_Z_R * a.n + i] = z_r;
         draws_out[SS_DRAW_U_DET * a.n + i] = u_det;
         draws_out[SS_DRAW_U_DET2 * a.n + i] = u_det2;
       }
-      bool valid = true, flag_c = false, flag_d = false, snr_ok = true, snr_r_ok = true;
-      if (MATH == SS_MATH_F64) {
-        // Stage 1: per band, the table look-ups (short, branchy).  Stage 2: the error /
-        // noise arithmetic of BOTH bands as one straight-line block of branch-free
-        // double-precision code, so that the two long dependency chains
-        // (10^x -> sqrt -> log10) interleave instead of running back to back.
-        double ext2[2], mt2[2], loge2[2], zf2[2], err2[2], mobs2[2];
-        bool bright2[2], have2[2], good2[2];
-        bool plain = true;
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          have2[b] = (b == SS_BAND_G) ? band_g : band_r;
-          const double mag = b == SS_BAND_G ? mag_g : mag_r;
-          const double maglim = b == SS_BAND_G ? ml_g : ml_r;
-          zf2[b] = b == SS_BAND_G ? z_g : z_r;
-          ext2[b] = __dmul_rn(p.coeff_extinc[b], ebv);                   // surveys.py:228
-          mt2[b] = __dadd_rn(mag, ext2[b]);                              // observed.py:167
-          bright2[b] = false;
-          loge2[b] = ss::nan_d();
-          if (!have2[b]) continue;
-          loge2[b] = ss::photo_error_log(p, tab, b, mt2[b], maglim, bright2[b]);  // surveys.py:234-286
-          plain = plain && fabs(mt2[b]) < 200.0 && !(fabs(loge2[b]) >= 300.0);
-          if (b == p.completeness_band) {                                // observed.py:224-243
-            flag_c = u_det <= ss::efficiency(p, p.completeness, tab, b, mt2[b], maglim);
-            if (p.perfect_galstarsep)
-              flag_d = u_det2 <= ss::efficiency(p, p.detection, tab, b, mt2[b], maglim);
-            SS_COUNT(SS_CNT_UNSEEN, maglim != maglim);
-          }
-        }
-        if (plain) {
-          // sample_measured_magnitudes (observed.py:863-904, :984-1035):
-          //   F = 3631*10^(-0.4 m), F_obs = F + (F*err/1.0857362)*z, m_obs = -2.5 log10(F_obs/3631)
-          // For magnitudes whose flux neither under- nor overflows this is, to rounding,
-          //   F_obs > 0  <=>  t > 0,   m_obs = m - 2.5 log10(t),   t = 1 + (err/1.0857362)*z
-          // which needs one log10 instead of exp10 + log10 + two divisions.
-#pragma unroll
-          for (int b = 0; b < 2; ++b) {
-            const double stat = bright2[b] ? p.err_bright : ss::exp10_nb(loge2[b]);
-            const double sys = p.sys_error[b];                           // surveys.py:288-290
-            err2[b] = ss::sqrt_nb(__dadd_rn(__dmul_rn(stat, stat), __dmul_rn(sys, sys)));
-            const double t = 1.0 + err2[b] * ss::kNum[11] * zf2[b];
-            good2[b] = t > 0.0;
-            mobs2[b] = good2[b] ? mt2[b] - 2.5 * ss::log10_nb(t) : ss::nan_d();
-          }
-        } else {
-#pragma unroll
-          for (int b = 0; b < 2; ++b) {
-            if (!have2[b]) continue;
-            err2[b] = ss::photo_error_total(p, b, loge2[b], bright2[b]);
-            mobs2[b] = ss::nan_d();
-            if (fabs(mt2[b]) < 200.0) {
-              const double t = 1.0 + err2[b] * ss::kNum[11] * zf2[b];
-              good2[b] = t > 0.0;
-              if (good2[b]) mobs2[b] = mt2[b] - 2.5 * log10(t);
-            } else {
-              const double flux = __dmul_rn(3631.0, exp10(__dmul_rn(-0.4, mt2[b])));
-              const double sig = __ddiv_rn(__dmul_rn(flux, err2[b]), 1.0857362);
-              const double fobs = __dadd_rn(flux, __dmul_rn(sig, zf2[b]));
-              good2[b] = fobs > 0.0;
-              if (good2[b]) mobs2[b] = __dmul_rn(-2.5, log10(__ddiv_rn(fobs, 3631.0)));
-            }
-          }
-        }
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          if (!have2[b]) continue;
-          const bool good = good2[b];
-          double mobs = mobs2[b];
-          if (good && p.dust_correction) mobs = __dsub_rn(mobs, ext2[b]);  // observed.py:194-208
-          valid = valid && good;
-          SS_COUNT(b == SS_BAND_G ? SS_CNT_BADMAG_G : SS_CNT_BADMAG_R, !good);
-          if (p.snr_cut[b]) snr_ok = snr_ok && (err2[b] <= p.snr_err_max);   // observed.py:266-281
-          if (b == SS_BAND_R) snr_r_ok = (err2[b] <= p.snr_err_max);         // observed.py:283-286
-          put<OutT>(a.o.mag_obs[b], i, mobs);
-          put<OutT>(a.o.magerr[b], i, err2[b]);
-        }
-      } else {
-#pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        if (!(b == SS_BAND_G ? band_g : band_r)) continue;
-        const double mag = b == SS_BAND_G ? mag_g : mag_r;
-        const double maglim = b == SS_BAND_G ? ml_g : ml_r;
-        const double zf = b == SS_BAND_G ? z_g : z_r;
-        const double ext = __dmul_rn(p.coeff_extinc[b], ebv);          // surveys.py:228
-        const double m_true = __dadd_rn(mag, ext);                     // observed.py:167
-        bool bright;
-        const double loge = ss::photo_error_log(p, tab, b, m_true, maglim, bright);  // surveys.py:234-286
-        // sample_measured_magnitudes (observed.py:863-904, :984-1035):
-        //   F = 3631*10^(-0.4 m), F_obs = F + (F*err/1.0857362)*z, m_obs = -2.5 log10(F_obs/3631)
-        // For magnitudes whose flux neither under- nor overflows this is, to rounding,
-        //   F_obs > 0  <=>  t > 0,   m_obs = m - 2.5 log10(t),   t = 1 + (err/1.0857362)*z
-        // which needs one log10 instead of exp10 + log10 + two divisions.
-        double err;
-        bool good;
-        double mobs = ss::nan_d();
-        bool done = false;
-        if (MATH == SS_MATH_MIXED) {
-          // fp32 fast path; falls through to the double path near a decision boundary
-          const float sys_f = (float)p.sys_error[b];
-          const float stat_f = bright ? (float)p.err_bright : exp2f((float)loge * 3.3219281f);
-          const float err_f = sqrtf(stat_f * stat_f + sys_f * sys_f);
-          const float thr_f = (float)p.snr_err_max;
-          const float x_f = err_f * (float)(1.0 / 1.0857362) * (float)zf;
-          const float t_f = 1.0f + x_f;
-          // err_f is good to ~1e-6 relative, so t_f carries ~1.5e-6 (1 + |x|) absolute error;
-          // the log amplifies it by 1/t: keep it below ~2.5e-4 mag (1e-5 of a magnitude ~25)
-          const bool safe = fabsf(err_f - thr_f) > 2e-5f * thr_f &&
-                            fabsf(t_f) > 0.012f * (1.0f + fabsf(x_f)) &&
-                            fabs(m_true) < 200.0;          // NaN anywhere -> not safe
-          if (safe) {
-            err = (double)err_f;
-            good = t_f > 0.0f;
-            if (good) mobs = m_true - (double)(0.75257499f * __log2f(t_f));   // 2.5 log10 t
-            done = true;
-          } else if (loge != loge || zf != zf) {
-            // unseen pixel (NaN depth) or NaN draw: the answer is NaN / BAD_MAG in any
-            // precision -- do not send 2 % of the stars (and half of the warps) down the
-            // double path
-            err = (loge != loge) ? loge : (double)err_f;
-            good = false;
-            done = true;
-          }
-        }
-        if (!done) {
-          err = ss::photo_error_total(p, b, loge, bright);                 // surveys.py:288-290
-          if (fabs(m_true) < 200.0) {
-            const double t = 1.0 + err * ss::kNum[11] * zf;
-            good = t > 0.0;
-            if (good) mobs = m_true - 2.5 * log10(t);
-          } else {
-            const double flux = __dmul_rn(3631.0, exp10(__dmul_rn(-0.4, m_true)));
-            const double sig = __ddiv_rn(__dmul_rn(flux, err), 1.0857362);
-            const double fobs = __dadd_rn(flux, __dmul_rn(sig, zf));
-            good = fobs > 0.0;
-            if (good) mobs = __dmul_rn(-2.5, log10(__ddiv_rn(fobs, 3631.0)));
-          }
-        }
-        if (good && p.dust_correction) mobs = __dsub_rn(mobs, ext);    // observed.py:194-208
-        valid = valid && good;
-        SS_COUNT(b == SS_BAND_G ? SS_CNT_BADMAG_G : SS_CNT_BADMAG_R, !good);
-        if (p.snr_cut[b]) snr_ok = snr_ok && (err <= p.snr_err_max);   // observed.py:266-281
-        if (b == SS_BAND_R) snr_r_ok = (err <= p.snr_err_max);         // observed.py:283-286
-        if (b == p.completeness_band) {                                // observed.py:224-243
-          flag_c = u_det <= ss::efficiency(p, p.completeness, tab, b, m_true, maglim);
-          if (p.perfect_galstarsep)
-            flag_d = u_det2 <= ss::efficiency(p, p.detection, tab, b, m_true, maglim);
-          SS_COUNT(SS_CNT_UNSEEN, maglim != maglim);
-        }
-        put<OutT>(a.o.mag_obs[b], i, mobs);
-        put<OutT>(a.o.magerr[b], i, err);
+      ss::ObsOut o;
+      ss::observe_star<MATH>(p, tab, share, band_g, band_r, mag_g, mag_r, ebv, ml_g, ml_r, z_g,
+                             z_r, u_det, u_det2, o);
+      SS_COUNT(SS_CNT_UNSEEN, o.unseen);
+      if (band_g) {
+        SS_COUNT(SS_CNT_BADMAG_G, o.bad[SS_BAND_G]);
+        put<OutT>(a.o.mag_obs[SS_BAND_G], i, o.mobs[SS_BAND_G]);
+        put<OutT>(a.o.magerr[SS_BAND_G], i, o.err[SS_BAND_G]);
       }
+      if (band_r) {
+        SS_COUNT(SS_CNT_BADMAG_R, o.bad[SS_BAND_R]);
+        put<OutT>(a.o.mag_obs[SS_BAND_R], i, o.mobs[SS_BAND_R]);
+        put<OutT>(a.o.magerr[SS_BAND_R], i, o.err[SS_BAND_R]);
       }
-      const bool observed = valid && flag_c && snr_ok;
-      const bool perfect = p.perfect_galstarsep && valid && flag_d && snr_ok && snr_r_ok;
-      if (a.o.flag_observed) a.o.flag_observed[i] = observed ? 1 : 0;
-      if (a.o.flag_perfect) a.o.flag_perfect[i] = perfect ? 1 : 0;
-      SS_COUNT(SS_CNT_OBSERVED, observed);
-      if (p.perfect_galstarsep) SS_COUNT(SS_CNT_PERFECT, perfect);
+      if (a.o.flag_observed) a.o.flag_observed[i] = o.observed ? 1 : 0;
+      if (a.o.flag_perfect) a.o.flag_perfect[i] = o.perfect ? 1 : 0;
+      SS_COUNT(SS_CNT_OBSERVED, o.observed);
+      if (p.perfect_galstarsep) SS_COUNT(SS_CNT_PERFECT, o.perfect);
     }
 
-    if (LEAN && i + stride < a.n) prepare(i + stride);
     if (want_hist) {
+      // only quantities this launch produced (or was handed) are binned
+      const bool have_pos = (ST & SS_STAGE_GENERATE) || (ST & SS_STAGE_ROTATE);
+      const bool have_dist = (ST & SS_STAGE_GENERATE) != 0;
+      const bool have_mag = (ST & SS_STAGE_GENERATE) || (ST & SS_STAGE_OBSERVE);
       const double hv[SS_N_HIST] = {phi1, phi2, dist, mag_g, mag_g - mag_r};
+      const bool hb[SS_N_HIST] = {have_pos, have_pos, have_dist, have_mag, have_mag};
 #pragma unroll
       for (int h = 0; h < SS_N_HIST; ++h) {
-        const double t = (hv[h] - p.hist_lo[h]) * p.hist_inv_width[h];
-        if (t >= 0.0 && t < (double)SS_HIST_BINS) atomicAdd(&s_hist[h * SS_HIST_BINS + (int)t], 1u);
+        if (!hb[h]) continue;
+        const int bin = ss::hist_bin((float)hv[h], (float)p.hist_lo[h], (float)p.hist_inv_width[h]);
+        if (bin >= 0) atomicAdd(&s_hist[h * SS_HIST_BINS + bin], 1u);
       }
     }
   }
@@ -799,6 +618,162 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
     for (int k = threadIdx.x; k < SS_N_COUNTERS; k += blockDim.x)
       if (s_cnt[k]) atomicAdd(&a.o.counters[k], (unsigned long long)s_cnt[k]);
     if (want_hist)
+      for (int k = threadIdx.x; k < SS_N_HIST * SS_HIST_BINS; k += blockDim.x)
+        if (s_hist[k]) atomicAdd(&a.o.counters[SS_N_COUNTERS + k], (unsigned long long)s_hist[k]);
+  }
+}
+
+// k_fused: the production kernel -- free-running generate -> rotate -> observe with the
+// phi1 grid table, the composite isochrone table, both bands, RING maps and the survey
+// curves in shared memory (the launcher checks all of that; anything else runs k_stars).
+// Same arithmetic as k_stars through the same device functions, so both produce the same
+// bytes (tests/test_gpu_parity.py::test_fused_kernel_equals_generic); what differs is the
+// schedule:
+//   * the star index is 32-bit inside a launch (ss_run splits longer ranges);
+//   * the POS Philox block of the NEXT star and its two bucket entries (phi1 table,
+//     isochrone table) are fetched at the end of an iteration, where few registers are
+//     live, so that their L2 round trip is over when the next iteration starts;
+//   * the phi1 histogram bin comes with the grid row; the other four are binned in fp32
+//     right after the generate stage, before the rotation raises the register pressure;
+//   * PACKED: the three survey maps interleaved as one 32-byte record per pixel -- one
+//     sector per star instead of three.
+template <typename OutT, int MATH, bool HIST, bool PACKED>
+__global__ void __launch_bounds__(SS_FUSED_BLOCK, SS_FUSED_MIN_CTAS)
+k_fused(const __grid_constant__ KArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_blob[];
+  __shared__ unsigned long long s_bar;
+  __shared__ unsigned int s_cnt[SS_N_COUNTERS];
+  __shared__ unsigned int s_hist[HIST ? SS_N_HIST * SS_HIST_BINS : 1];
+
+  const SSParams& p = a.p;
+  const bool want_cnt = a.o.counters != nullptr;
+  const int share = ss::curve_share(p);
+  for (int i = threadIdx.x; i < SS_N_COUNTERS; i += blockDim.x) s_cnt[i] = 0;
+  if (HIST)
+    for (int i = threadIdx.x; i < SS_N_HIST * SS_HIST_BINS; i += blockDim.x) s_hist[i] = 0;
+  stage_blob(smem_blob, a.t.blob, a.blob_bytes, &s_bar);
+  const double* const tab = reinterpret_cast<const double*>(smem_blob);
+  __syncthreads();
+
+  const uint32_t n = (uint32_t)a.n;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const double2* __restrict__ const grid_lut = reinterpret_cast<const double2*>(a.t.grid_lut);
+  const double2* __restrict__ const iso_lut = reinterpret_cast<const double2*>(a.t.iso_lut);
+  const uint32_t grid_lut_n = (uint32_t)p.grid_lut_n, iso_lut_n = (uint32_t)p.iso_lut_n;
+
+  uint4 wp = make_uint4(0u, 0u, 0u, 0u);
+  double2 eg = make_double2(0.0, 0.0), ei = make_double2(0.0, 0.0);
+  auto prepare = [&](uint32_t star) {
+    wp = ss::philox_block(a.offset + star, SS_DRAW_BLOCK_POS, a.seed);
+    // bucket = floor(u * buckets), u = w / 2^32, buckets a power of two: the high word of w * buckets
+    eg = __ldg(&grid_lut[__umulhi(wp.x, grid_lut_n)]);
+    ei = __ldg(&iso_lut[__umulhi(wp.y, iso_lut_n)]);
+  };
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) prepare(i);
+  for (; i < n; i += stride) {
+    // ------------------------------------------------ generate (model.py:106-157)
+    const double u_phi1 = ss::u32(wp.x), u_mass = ss::u32(wp.y);
+    GridRow row;
+    {
+      const long long packed = __double_as_longlong(eg.x);
+      const int lo = (int)(packed & 0xffffffffLL), k = (int)(packed >> 32);
+      int idx = lo + ((k == 1 && u_phi1 >= eg.y) ? 1 : 0);
+      if (k > 1) idx = step_scan(a.t.grid_thr, lo, k, u_phi1, grid_lut_n);
+      idx = (u_phi1 > p.cdf_last) ? p.grid_nthr + 1 : idx;          // interp1d fill_value = 0.0
+      load_grid_row(a.t.grid_rows, idx, row);
+    }
+    double m1, m2;
+    {
+      const long long packed = __double_as_longlong(ei.x);
+      const int lo = (int)(packed & 0xffffffffLL), k = (int)(packed >> 32);
+      int idx = lo + ((k == 1 && u_mass >= ei.y) ? 1 : 0);
+      if (k > 1) idx = step_scan(a.t.iso_thr, lo, k, u_mass, iso_lut_n);
+      iso_row_eval(a.t.iso_rows, idx, u_mass, m1, m2);
+    }
+    float zf_phi2, zf_dist;
+    ss::bm32f(wp.z, wp.w, zf_phi2, zf_dist);
+    if (!(row.s >= 0.0) || !(row.ds >= 0.0)) {                      // scipy: scale must be >= 0
+      if (want_cnt) atomicAdd(&s_cnt[SS_CNT_DOMAIN], (row.s >= 0.0 ? 0u : 1u) + (row.ds >= 0.0 ? 0u : 1u));
+    }
+    const double phi2 = __dadd_rn(__dmul_rn((double)zf_phi2, row.s), row.c);
+    const double dist = __dadd_rn(__dmul_rn((double)zf_dist, row.ds), row.dc);
+    const double mag_g = __dadd_rn(m1, dist), mag_r = __dadd_rn(m2, dist);
+    put<OutT>(a.o.phi1, i, row.x);
+    put<OutT>(a.o.phi2, i, phi2);
+    put<OutT>(a.o.dist, i, dist);
+    put<OutT>(a.o.mag[SS_BAND_G], i, mag_g);
+    put<OutT>(a.o.mag[SS_BAND_R], i, mag_r);
+    if (HIST) {
+      const int b0 = __double2loint(row.thr);                        // host-binned phi1
+      if (b0 >= 0) atomicAdd(&s_hist[b0], 1u);
+      const float hv[4] = {(float)phi2, (float)dist, (float)mag_g, (float)(mag_g - mag_r)};
+#pragma unroll
+      for (int h = 1; h < SS_N_HIST; ++h) {
+        const int bin = ss::hist_bin(hv[h - 1], (float)p.hist_lo[h], (float)p.hist_inv_width[h]);
+        if (bin >= 0) atomicAdd(&s_hist[h * SS_HIST_BINS + bin], 1u);
+      }
+    }
+
+    // ------------------------------------------------ rotate (observed.py:573)
+    double wx, wy, wz, lon, ra, dec;
+    rotate_star(p, row.sinx, row.cosx, phi2, wx, wy, wz, lon, ra, dec);
+    put<OutT>(a.o.ra, i, ra);
+    put<OutT>(a.o.dec, i, dec);
+
+    // ------------------------------------------------ observe (observed.py:146-291)
+    ss::HpLoc L;
+    if (fabs(wz) < 0.9999 && lon == lon) L = ss::hp_from_vector(wz, lon);
+    else L = ss::hp_locate(ra, dec);
+    double ebv = ss::nan_d(), ml_g = ss::nan_d(), ml_r = ss::nan_d();
+    if (L.valid) {
+      const long long pe = ss::hp_ring(L, p.nside_ebv);
+      if (PACKED) {
+        const double2* __restrict__ rec = reinterpret_cast<const double2*>(a.m.packed) + 2 * pe;
+        const double2 r0 = __ldg(rec), r1 = __ldg(rec + 1);
+        ebv = r0.x; ml_g = r0.y; ml_r = r1.x;
+      } else {
+        ebv = __ldg(&a.m.ebv[pe]);
+        const long long pg = (p.nside_maglim[SS_BAND_G] == p.nside_ebv)
+                                 ? pe : ss::hp_ring(L, p.nside_maglim[SS_BAND_G]);
+        ml_g = __ldg(&a.m.maglim[SS_BAND_G][pg]);
+        const long long pr = (p.nside_maglim[SS_BAND_R] == p.nside_ebv) ? pe
+                             : (p.nside_maglim[SS_BAND_R] == p.nside_maglim[SS_BAND_G])
+                                 ? pg : ss::hp_ring(L, p.nside_maglim[SS_BAND_R]);
+        ml_r = __ldg(&a.m.maglim[SS_BAND_R][pr]);
+      }
+      if (a.o.pix) a.o.pix[i] = (p.nside_pix == p.nside_ebv) ? pe : ss::hp_ring(L, p.nside_pix);
+    } else {
+      if (want_cnt) atomicAdd(&s_cnt[SS_CNT_BADCOORD], 1u);
+      if (a.o.pix) a.o.pix[i] = -1;
+    }
+    const uint4 wo = ss::philox_block(a.offset + i, SS_DRAW_BLOCK_OBS, a.seed);
+    double z_r, z_g;
+    ss::bm32(wo.x, wo.y, z_r, z_g);
+    ss::ObsOut o;
+    ss::observe_star<MATH>(p, tab, share, true, true, mag_g, mag_r, ebv, ml_g, ml_r, z_g, z_r,
+                           ss::u32(wo.z), ss::u32(wo.w), o);
+    put<OutT>(a.o.mag_obs[SS_BAND_G], i, o.mobs[SS_BAND_G]);
+    put<OutT>(a.o.magerr[SS_BAND_G], i, o.err[SS_BAND_G]);
+    put<OutT>(a.o.mag_obs[SS_BAND_R], i, o.mobs[SS_BAND_R]);
+    put<OutT>(a.o.magerr[SS_BAND_R], i, o.err[SS_BAND_R]);
+    if (a.o.flag_observed) a.o.flag_observed[i] = o.observed ? 1 : 0;
+    if (a.o.flag_perfect) a.o.flag_perfect[i] = o.perfect ? 1 : 0;
+    SS_COUNT(SS_CNT_UNSEEN, o.unseen);
+    SS_COUNT(SS_CNT_BADMAG_G, o.bad[SS_BAND_G]);
+    SS_COUNT(SS_CNT_BADMAG_R, o.bad[SS_BAND_R]);
+    SS_COUNT(SS_CNT_OBSERVED, o.observed);
+    if (p.perfect_galstarsep) SS_COUNT(SS_CNT_PERFECT, o.perfect);
+
+    if (i + stride < n && i + stride > i) prepare(i + stride);
+  }
+
+  if (want_cnt) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&a.o.counters[SS_CNT_TOTAL], a.n);
+    __syncthreads();
+    for (int k = threadIdx.x; k < SS_N_COUNTERS; k += blockDim.x)
+      if (s_cnt[k]) atomicAdd(&a.o.counters[k], (unsigned long long)s_cnt[k]);
+    if (HIST)
       for (int k = threadIdx.x; k < SS_N_HIST * SS_HIST_BINS; k += blockDim.x)
         if (s_hist[k]) atomicAdd(&a.o.counters[SS_N_COUNTERS + k], (unsigned long long)s_hist[k]);
   }
@@ -882,6 +857,65 @@ __global__ void k_math_probe(int fn, const double* x, const double* y2, double* 
   }
 }
 
+// rv.rvs(loc, scale): draw * scale + loc per element (reference samplers.py:94-138); the
+// draw is injected or the star's z_phi2 / u_phi2 (POS block words 2, 3)
+__global__ void k_loc_scale(int normal, const double* loc, const double* scale, double loc0,
+                            double scale0, const double* draws, double* out, unsigned long long n,
+                            unsigned long long offset, unsigned long long seed) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += stride) {
+    double d;
+    if (draws) {
+      d = draws[i];
+    } else {
+      const uint4 w = ss::philox_block(offset + i, SS_DRAW_BLOCK_POS, seed);
+      double z0, z1;
+      ss::bm32(w.z, w.w, z0, z1);
+      d = normal ? z0 : ss::u32(w.z);
+    }
+    out[i] = __dadd_rn(__dmul_rn(d, scale ? scale[i] : scale0), loc ? loc[i] : loc0);
+  }
+}
+
+// StreamInjector.sample_measured_magnitudes (reference observed.py:863-904, :984-1035) as
+// written -- flux-space Gaussian noise, NaN where the noisy flux is not positive ("BAD_MAG");
+// z injected or the star's z_r (OBS block words 0, 1)
+__global__ void k_noisy_mag(const double* mag, const double* err, const double* z_in, double* out,
+                            unsigned long long n, unsigned long long offset,
+                            unsigned long long seed) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += stride) {
+    double z;
+    if (z_in) {
+      z = z_in[i];
+    } else {
+      const uint4 w = ss::philox_block(offset + i, SS_DRAW_BLOCK_OBS, seed);
+      double z1;
+      ss::bm32(w.x, w.y, z, z1);
+    }
+    const double flux = __dmul_rn(3631.0, exp10(__dmul_rn(-0.4, mag[i])));
+    const double sig = __ddiv_rn(__dmul_rn(flux, err[i]), 1.0857362);
+    const double fobs = __dadd_rn(flux, __dmul_rn(sig, z));
+    out[i] = (fobs > 0.0) ? __dmul_rn(-2.5, log10(__ddiv_rn(fobs, 3631.0))) : ss::nan_d();
+  }
+}
+
+// Bernoulli trial u <= prob (reference observed.py:906-959); u injected or the star's u_det
+// (OBS block word 2)
+__global__ void k_bernoulli(const double* prob, const double* u_in, uint8_t* out,
+                            unsigned long long n, unsigned long long offset,
+                            unsigned long long seed) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += stride) {
+    const double u = u_in ? u_in[i]
+                          : ss::u32(ss::philox_block(offset + i, SS_DRAW_BLOCK_OBS, seed).z);
+    out[i] = (u <= prob[i]) ? 1 : 0;
+  }
+}
+
 // ---------------------------------------------------------------- host side
 struct DevInfo {
   int device = -1, sms = 0, smem_optin = 0;
@@ -900,24 +934,22 @@ int device_info(DevInfo& d) {
   return SS_OK;
 }
 
-// static shared memory of k_stars (barrier + counters + histograms), rounded up
+// static shared memory of the star kernels (barrier + counters + histograms), rounded up
 constexpr int kStaticSmem = 8 + 4 * SS_N_COUNTERS + 4 * SS_N_HIST * SS_HIST_BINS + 256;
 
 int plan_launch(const DevInfo& d, int64_t blob_bytes, uint64_t n, int& smem, int& grid) {
   smem = (blob_bytes > 0 && blob_bytes + kStaticSmem <= d.smem_optin) ? (int)blob_bytes : 0;
   const uint64_t blocks_needed = (n + SS_BLOCK - 1) / SS_BLOCK;
-  // persistent CTAs, as many as are resident per SM: a 1024-thread CTA at 64 registers
-  // per thread owns the whole register file, smaller CTAs pair up when shared memory allows
-  int per_sm = 1;
-  if (SS_BLOCK <= 512 && smem + kStaticSmem <= d.smem_optin / 2) per_sm = 2;
-  const uint64_t cap = (uint64_t)d.sms * per_sm;
+  // persistent CTAs, one per SM: a 1024-thread CTA at 64 registers per thread owns the
+  // whole register file
+  const uint64_t cap = (uint64_t)d.sms;
   grid = (int)(blocks_needed < cap ? (blocks_needed ? blocks_needed : 1) : cap);
   return SS_OK;
 }
 
-template <uint32_t ST, typename OutT, bool LEAN = false, int MATH = SS_MATH_F64>
-int launch_t(const KArgs& a, int smem, int grid, cudaStream_t stream) {
-  // the opt-in dynamic shared-memory limit is a per-device, per-kernel attribute
+// the opt-in dynamic shared-memory limit is a per-device, per-kernel attribute
+template <typename K>
+int launch_kernel(K kern, const KArgs& a, int smem, int grid, int block, cudaStream_t stream) {
   static thread_local int configured_smem[64];
   static thread_local bool init = false;
   if (!init) {
@@ -926,39 +958,73 @@ int launch_t(const KArgs& a, int smem, int grid, cudaStream_t stream) {
   }
   int dev = 0;
   SS_CUDA(cudaGetDevice(&dev));
-  auto kern = k_stars<ST, OutT, LEAN, MATH>;
   if (dev < 0 || dev >= 64 || smem > configured_smem[dev]) {
     SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     if (dev >= 0 && dev < 64) configured_smem[dev] = smem;
   }
-  kern<<<grid, SS_BLOCK, smem, stream>>>(a);
+  kern<<<grid, block, smem, stream>>>(a);
   SS_CUDA(cudaGetLastError());
   return SS_OK;
 }
 
+template <uint32_t ST, typename OutT, int MATH = SS_MATH_F64>
+int launch_t(const KArgs& a, int smem, int grid, cudaStream_t stream) {
+  return launch_kernel(k_stars<ST, OutT, MATH>, a, smem, grid, SS_BLOCK, stream);
+}
+
+// the production kernel's preconditions (see k_fused)
+bool fused_eligible(const KArgs& a, int smem) {
+  const SSParams& p = a.p;
+  const SSDraws& d = a.d;
+  return p.fused_kernel && smem > 0 && p.density_kind == SS_DENSITY_GRID && !p.nest && p.has_dist &&
+         p.has_iso && p.iso_direct && p.band_present[0] && p.band_present[1] &&
+         p.track_sampler == SS_SAMPLER_GAUSSIAN && p.dist_sampler == SS_SAMPLER_GAUSSIAN &&
+         !d.u_phi1 && !d.u_mass && !d.n_phi2 && !d.n_dist && !d.z_flux[0] && !d.z_flux[1] &&
+         !d.u_det && !d.u_det2 && !a.in.phi1 && !a.in.phi2 && !a.in.dist && !a.o.draws_out &&
+         a.n <= (1ULL << 31);
+}
+
+template <typename OutT, int MATH, bool HIST>
+int launch_fused_p(const KArgs& a, int smem, int grid, cudaStream_t s) {
+  const SSParams& p = a.p;
+  const bool packed = a.m.packed && a.m.nside_packed == p.nside_ebv &&
+                      p.nside_maglim[0] == p.nside_ebv && p.nside_maglim[1] == p.nside_ebv;
+  return packed ? launch_kernel(k_fused<OutT, MATH, HIST, true>, a, smem, grid, SS_FUSED_BLOCK, s)
+                : launch_kernel(k_fused<OutT, MATH, HIST, false>, a, smem, grid, SS_FUSED_BLOCK, s);
+}
+
 template <typename OutT>
-int launch_stage(uint32_t st, const KArgs& a, int smem, int grid, cudaStream_t s) {
+int launch_fused(const KArgs& a, const DevInfo& d, int smem, cudaStream_t s) {
+  const uint64_t blocks_needed = (a.n + SS_FUSED_BLOCK - 1) / SS_FUSED_BLOCK;
+  const uint64_t cap = (uint64_t)d.sms * SS_FUSED_MIN_CTAS;
+  const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
+  const bool hist = a.o.counters && a.p.hist_enable;
+  if (a.p.math_mode == SS_MATH_FAST)
+    return hist ? launch_fused_p<OutT, SS_MATH_FAST, true>(a, smem, grid, s)
+                : launch_fused_p<OutT, SS_MATH_FAST, false>(a, smem, grid, s);
+  return hist ? launch_fused_p<OutT, SS_MATH_F64, true>(a, smem, grid, s)
+              : launch_fused_p<OutT, SS_MATH_F64, false>(a, smem, grid, s);
+}
+
+template <typename OutT>
+int launch_stage(uint32_t st, const KArgs& a, const DevInfo& d, int smem, int grid, cudaStream_t s) {
+  const bool fast = a.p.math_mode == SS_MATH_FAST;
+#ifdef SS_DEV_BUILD
+  if (st != 7) return fail(SS_EINVAL, "development build: fused stage mask only%s");
+  {
+#else
   switch (st) {
     case 1: return launch_t<1, OutT>(a, smem, grid, s);
     case 2: return launch_t<2, OutT>(a, smem, grid, s);
     case 3: return launch_t<3, OutT>(a, smem, grid, s);
-    case 4:
-      return a.p.math_mode == SS_MATH_MIXED ? launch_t<4, OutT, false, SS_MATH_MIXED>(a, smem, grid, s)
-                                            : launch_t<4, OutT>(a, smem, grid, s);
-    case 6: return launch_t<6, OutT>(a, smem, grid, s);
-    case 7: {
-      const SSDraws& d = a.d;
-      const bool lean = a.p.density_kind == SS_DENSITY_GRID && !a.p.nest && a.p.has_dist &&
-                        a.p.has_iso && a.p.iso_direct && a.p.band_present[0] && a.p.band_present[1] &&
-                        !d.u_phi1 && !d.u_mass && !d.n_phi2 && !d.n_dist && !d.z_flux[0] &&
-                        !d.z_flux[1] && !d.u_det && !d.u_det2 && !a.in.phi1 && !a.in.phi2 &&
-                        !a.in.dist && !a.o.draws_out;
-      if (a.p.math_mode == SS_MATH_MIXED)
-        return (lean && smem > 0) ? launch_t<7, OutT, true, SS_MATH_MIXED>(a, smem, grid, s)
-                                  : launch_t<7, OutT, false, SS_MATH_MIXED>(a, smem, grid, s);
-      return (lean && smem > 0) ? launch_t<7, OutT, true>(a, smem, grid, s)
-                                : launch_t<7, OutT, false>(a, smem, grid, s);
-    }
+    case 4: return fast ? launch_t<4, OutT, SS_MATH_FAST>(a, smem, grid, s) : launch_t<4, OutT>(a, smem, grid, s);
+    case 6: return fast ? launch_t<6, OutT, SS_MATH_FAST>(a, smem, grid, s) : launch_t<6, OutT>(a, smem, grid, s);
+    case 7:
+#endif
+      if (fused_eligible(a, smem) &&
+          (SS_FUSED_MIN_CTAS == 1 || SS_FUSED_MIN_CTAS * (smem + kStaticSmem + 1024) <= d.smem_optin))
+        return launch_fused<OutT>(a, d, smem, s);
+      return fast ? launch_t<7, OutT, SS_MATH_FAST>(a, smem, grid, s) : launch_t<7, OutT>(a, smem, grid, s);
   }
   return fail(SS_EINVAL, "unsupported stage mask%s");
 }
@@ -980,10 +1046,8 @@ int validate(uint32_t st, const SSParams* p, const SSTables* t, const SSMaps* m,
   if (!p || !out) return fail(SS_EINVAL, "params and out must not be NULL%s");
   if (out->dtype != SS_DTYPE_F64 && out->dtype != SS_DTYPE_F32)
     return fail(SS_EINVAL, "SSOut.dtype must be SS_DTYPE_F64 or SS_DTYPE_F32%s");
-  if (p->math_mode != SS_MATH_F64 && p->math_mode != SS_MATH_MIXED)
-    return fail(SS_EINVAL, "SSParams.math_mode must be SS_MATH_F64 or SS_MATH_MIXED%s");
-  if (p->math_mode == SS_MATH_MIXED && st != 4 && st != 7)
-    return fail(SS_EINVAL, "SS_MATH_MIXED is available for the observe and fused stage masks%s");
+  if (p->math_mode != SS_MATH_F64 && p->math_mode != SS_MATH_FAST)
+    return fail(SS_EINVAL, "SSParams.math_mode must be SS_MATH_F64 or SS_MATH_FAST%s");
   const int64_t nd = t ? t->blob_bytes / 8 : 0;
   if (t && (t->blob_bytes % 16 != 0)) return fail(SS_EINVAL, "blob_bytes must be a multiple of 16%s");
   if (t && (t->blob_hot_bytes % 16 != 0 || t->blob_hot_bytes < 0 || t->blob_hot_bytes > t->blob_bytes))
@@ -1117,8 +1181,12 @@ int ss_run(uint32_t stages, const SSParams* p, const SSTables* t, const SSMaps* 
   a.blob_bytes = (uint32_t)a.t.blob_hot_bytes;                 // what stage_blob copies
   if (!a.blob_in_smem) a.t.blob_hot_bytes = a.t.blob_bytes;   // everything read from global
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  return out->dtype == SS_DTYPE_F32 ? launch_stage<float>(stages, a, smem, grid, s)
-                                    : launch_stage<double>(stages, a, smem, grid, s);
+#ifdef SS_DEV_BUILD   // quick experiments: the double-output kernels only
+  return launch_stage<double>(stages, a, dev, smem, grid, s);
+#else
+  return out->dtype == SS_DTYPE_F32 ? launch_stage<float>(stages, a, dev, smem, grid, s)
+                                    : launch_stage<double>(stages, a, dev, smem, grid, s);
+#endif
 }
 
 int ss_generate(const SSParams* p, const SSTables* t, const SSDraws* d, const SSOut* out,
@@ -1240,6 +1308,41 @@ int ss_math_probe(int32_t fn, const double* x, const double* y2, double* out, ui
   return SS_OK;
 }
 
+int ss_loc_scale(int32_t normal, const double* loc, const double* scale, double loc0,
+                 double scale0, const double* draws, double* out, uint64_t n, uint64_t star_offset,
+                 uint64_t seed, void* stream) {
+  if (!out) return fail(SS_EINVAL, "ss_loc_scale: out is NULL%s");
+  if (n == 0) return SS_OK;
+  int grid, rc;
+  if ((rc = small_grid(n, &grid))) return rc;
+  k_loc_scale<<<grid, 256, 0, (cudaStream_t)stream>>>(normal, loc, scale, loc0, scale0, draws, out,
+                                                      n, star_offset, seed);
+  SS_CUDA(cudaGetLastError());
+  return SS_OK;
+}
+
+int ss_noisy_magnitudes(const double* mag, const double* err, const double* z, double* out,
+                        uint64_t n, uint64_t star_offset, uint64_t seed, void* stream) {
+  if (!mag || !err || !out) return fail(SS_EINVAL, "ss_noisy_magnitudes: bad argument%s");
+  if (n == 0) return SS_OK;
+  int grid, rc;
+  if ((rc = small_grid(n, &grid))) return rc;
+  k_noisy_mag<<<grid, 256, 0, (cudaStream_t)stream>>>(mag, err, z, out, n, star_offset, seed);
+  SS_CUDA(cudaGetLastError());
+  return SS_OK;
+}
+
+int ss_bernoulli(const double* prob, const double* u, uint8_t* out, uint64_t n,
+                 uint64_t star_offset, uint64_t seed, void* stream) {
+  if (!prob || !out) return fail(SS_EINVAL, "ss_bernoulli: bad argument%s");
+  if (n == 0) return SS_OK;
+  int grid, rc;
+  if ((rc = small_grid(n, &grid))) return rc;
+  k_bernoulli<<<grid, 256, 0, (cudaStream_t)stream>>>(prob, u, out, n, star_offset, seed);
+  SS_CUDA(cudaGetLastError());
+  return SS_OK;
+}
+
 // ---------------------------------------------------------------- host-buffer variants
 namespace {
 struct ColSpec { size_t off_out; int is_float; };  // float-typed column (dtype) or fixed type
@@ -1255,10 +1358,15 @@ int64_t ss_host_workspace_bytes(uint64_t chunk, int32_t dtype) {
   return (int64_t)(2 * per + align256(SS_COUNTERS_LEN * 8));
 }
 
+// two private streams (kernel / copies) and their events, created once per host thread and
+// device and kept for the life of the thread
 struct HostPipe {
+  int device = -1;
   cudaStream_t compute = nullptr, copy = nullptr;
   cudaEvent_t done[2] = {nullptr, nullptr}, drained[2] = {nullptr, nullptr}, loaded[2] = {nullptr, nullptr};
-  int init() {
+  int init(int dev) {
+    if (device == dev) return SS_OK;
+    release();
     SS_CUDA(cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking));
     SS_CUDA(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
@@ -1266,32 +1374,29 @@ struct HostPipe {
       SS_CUDA(cudaEventCreateWithFlags(&drained[i], cudaEventDisableTiming));
       SS_CUDA(cudaEventCreateWithFlags(&loaded[i], cudaEventDisableTiming));
     }
+    device = dev;
     return SS_OK;
   }
-  ~HostPipe() {
+  void release() {
     for (int i = 0; i < 2; ++i) {
       if (done[i]) cudaEventDestroy(done[i]);
       if (drained[i]) cudaEventDestroy(drained[i]);
       if (loaded[i]) cudaEventDestroy(loaded[i]);
+      done[i] = drained[i] = loaded[i] = nullptr;
     }
     if (compute) cudaStreamDestroy(compute);
     if (copy) cudaStreamDestroy(copy);
+    compute = copy = nullptr;
+    device = -1;
   }
+  // no destructor: at thread / process exit the CUDA context may already be gone
 };
 
-static int host_pipeline(uint32_t stages, const SSParams* p, const SSTables* t, const SSMaps* m,
-                         const SSCatalog* in_host, const SSOut* oh, uint64_t n,
-                         uint64_t star_offset, uint64_t seed, void* workspace,
-                         int64_t workspace_bytes, uint64_t chunk) {
-  if (!oh || !workspace) return fail(SS_EINVAL, "host variant: out and workspace are required%s");
-  if (chunk == 0) return fail(SS_EINVAL, "chunk must be > 0%s");
-  if (workspace_bytes < ss_host_workspace_bytes(chunk, oh->dtype))
-    return fail(SS_EINVAL, "workspace too small (see ss_host_workspace_bytes)%s");
+static int host_pipeline_body(HostPipe& pipe, uint32_t stages, const SSParams* p, const SSTables* t,
+                              const SSMaps* m, const SSCatalog* in_host, const SSOut* oh, uint64_t n,
+                              uint64_t star_offset, uint64_t seed, void* workspace, uint64_t chunk) {
   const size_t es = elem_size(oh->dtype);
-  HostPipe pipe;
-  int rc = pipe.init();
-  if (rc) return rc;
-
+  int rc;
   // carve the workspace
   char* base = (char*)workspace;
   uint64_t cur = 0;
@@ -1377,6 +1482,36 @@ static int host_pipeline(uint32_t stages, const SSParams* p, const SSTables* t, 
   }
   SS_CUDA(cudaStreamSynchronize(pipe.copy));
   return SS_OK;
+}
+
+static int host_pipeline(uint32_t stages, const SSParams* p, const SSTables* t, const SSMaps* m,
+                         const SSCatalog* in_host, const SSOut* oh, uint64_t n,
+                         uint64_t star_offset, uint64_t seed, void* workspace,
+                         int64_t workspace_bytes, uint64_t chunk) {
+  if (!oh || !workspace) return fail(SS_EINVAL, "host variant: out and workspace are required%s");
+  if (chunk == 0) return fail(SS_EINVAL, "chunk must be > 0%s");
+  if (workspace_bytes < ss_host_workspace_bytes(chunk, oh->dtype))
+    return fail(SS_EINVAL, "workspace too small (see ss_host_workspace_bytes)%s");
+  static thread_local HostPipe pipe;
+  int dev = 0;
+  SS_CUDA(cudaGetDevice(&dev));
+  int rc = pipe.init(dev);
+  if (rc) return rc;
+  // The call is synchronous and works on private streams: everything the caller queued
+  // before it (table / map uploads, the allocation that produced the workspace, earlier
+  // readers of the host buffers) must have finished first.
+  SS_CUDA(cudaDeviceSynchronize());
+  rc = host_pipeline_body(pipe, stages, p, t, m, in_host, oh, n, star_offset, seed, workspace, chunk);
+  if (rc) {
+    // copies into the caller's buffers may still be in flight: let them land (or fail)
+    // before the caller can free anything; keep the first error's message
+    char keep[sizeof(g_err)];
+    memcpy(keep, g_err, sizeof(keep));
+    cudaStreamSynchronize(pipe.compute);
+    cudaStreamSynchronize(pipe.copy);
+    memcpy(g_err, keep, sizeof(keep));
+  }
+  return rc;
 }
 
 int ss_generate_observe_host(const SSParams* p, const SSTables* t, const SSMaps* m,

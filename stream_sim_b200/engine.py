@@ -254,6 +254,40 @@ def snr_error_threshold(snr_min=SNR_MIN):
     return float(e)
 
 
+def snr_loge_threshold(sys_error, snr_min=SNR_MIN):
+    """The SNR cut decided on x = log10(statistical error) (``SSParams.snr_loge_max``):
+    ``magerr(x) = sqrt((10**x)**2 + sys**2)`` is monotone in x, so
+    ``1.0/magerr >= snr_min`` (reference observed.py:278-279 on surveys.py:274-290) holds
+    exactly for x <= x*, the largest double for which NumPy's own arithmetic passes;
+    found by bisection on the bit patterns.  NaN when no x passes."""
+    def passes(x):
+        with np.errstate(over="ignore", divide="ignore"):
+            stat = 10 ** np.atleast_1d(np.asarray(x, dtype=float))
+            return 1.0 / np.sqrt(stat ** 2 + sys_error ** 2) >= snr_min
+    lo, hi = -300.0, 300.0
+    if not passes(lo)[0]:
+        return float("nan")
+    if passes(hi)[0]:
+        return float("inf")
+    # bit patterns of doubles are ordered like the doubles on each side of zero: bisect the
+    # value first, then walk the last bits
+    for _ in range(200):
+        mid = 0.5 * (lo + hi)
+        if mid == lo or mid == hi:
+            break
+        if passes(mid)[0]:
+            lo = mid
+        else:
+            hi = mid
+    assert np.nextafter(lo, np.inf) == hi and passes(lo)[0] and not passes(hi)[0]
+    # monotone around the threshold as far as NumPy's pow is concerned
+    near = lo + np.arange(-64, 65) * np.spacing(lo)
+    ok = passes(near)
+    if not (ok[:65].all() and not ok[65:].any()):
+        raise AssertionError("10**x is not monotone around the SNR threshold")
+    return float(lo)
+
+
 def frame_matrix(frame):
     """3x3 ICRS->stream rotation from a GreatCircleFrame, ndarray or None."""
     if frame is None:
@@ -284,7 +318,8 @@ class StarEngine:
     def __init__(self, stream=None, survey=None, frame=None, device=None, bands=("r", "g"),
                  nside=4096, dust_correction=True, perfect_galstarsep=False,
                  detection_mag_cut=("g",), nest=False, hist=None, cdf_steps=1e5,
-                 grid_table=True, math="f64", iso_direct=True):
+                 grid_table=True, math="f64", iso_direct=True, fused_kernel=True,
+                 packed_maps="auto"):
         torch = _torch()
         self.lib = _lib.load()
         self.device = require_device(device)
@@ -302,16 +337,18 @@ class StarEngine:
         p = self.params
         self._grid_table = bool(grid_table)
         self._iso_direct = bool(iso_direct)
-        if math not in ("f64", "mixed"):
-            raise ValueError("math must be 'f64' or 'mixed'")
-        self.params.math_mode = _lib.MATH_MIXED if math == "mixed" else _lib.MATH_F64
+        if math not in ("f64", "fast"):
+            raise ValueError("math must be 'f64' or 'fast'")
+        self.params.math_mode = _lib.MATH_FAST if math == "fast" else _lib.MATH_F64
+        self.params.fused_kernel = int(bool(fused_kernel))
+        self._packed_maps = packed_maps
+        self._describe_hist(hist)          # before the stream: the phi1 grid rows carry their bin
         if survey is not None:
             self._describe_survey(survey, hot, bands, nside, dust_correction,
                                   perfect_galstarsep, detection_mag_cut, nest)
         if stream is not None:
             self._describe_stream(stream, hot, cold, int(cdf_steps))
         self.set_frame(frame)
-        self._describe_hist(hist)
         hot_blob, cold_blob = hot.finalize(), cold.finalize()
         base = hot_blob.size // 8
         for f in (p.track_center, p.track_spread, p.dist_center, p.dist_spread):
@@ -474,8 +511,11 @@ class StarEngine:
                 dc = ds = np.zeros(len(x))
         rad = np.radians(x)
         thr_full = np.concatenate([thr, [np.inf]])
-        rows = np.stack([np.concatenate([thr_full, [np.inf]]), x, c, s, dc, ds, np.sin(rad),
-                         np.cos(rad)], axis=1)
+        # column 0 is not read as a number by any kernel: its low 32 bits carry the phi1
+        # histogram bin of the row's x (the production kernel never bins phi1 itself)
+        col0 = np.zeros(len(x), dtype=np.int64)
+        col0[:] = self.hist_bin("phi1", x).astype(np.int64) & 0xFFFFFFFF
+        rows = np.stack([col0.view(np.float64), x, c, s, dc, ds, np.sin(rad), np.cos(rad)], axis=1)
         edges = np.searchsorted(thr, np.arange(GRID_LUT + 1) / GRID_LUT, side="right")
         lo, k = edges[:-1].astype(np.int64), np.diff(edges).astype(np.int64)
         lut = np.empty((GRID_LUT, 2), dtype=np.float64)
@@ -540,6 +580,7 @@ class StarEngine:
             return t
 
         ebv = device_map(survey.ebv_map)
+        self._map_tensors = {"ebv": ebv}
         p.nside_ebv = npix2nside(ebv.numel())
         self.maps.ebv = ebv.data_ptr()
         for band in ("g", "r"):
@@ -551,6 +592,7 @@ class StarEngine:
             if band not in survey.coeff_extinc:
                 raise ValueError(f"Band '{band}' not available. Available: {survey.bands}")
             ml = device_map(survey.maglim_maps[band])
+            self._map_tensors[band] = ml
             p.band_present[b] = 1
             p.nside_maglim[b] = npix2nside(ml.numel())
             self.maps.maglim[b] = ml.data_ptr()
@@ -558,18 +600,59 @@ class StarEngine:
             p.saturation[b] = float(survey.saturation[band])
             p.sys_error[b] = float(survey.sys_error.get(band, 0.005))
             p.snr_cut[b] = int(band in detection_mag_cut)
+            p.snr_loge_max[b] = snr_loge_threshold(p.sys_error[b])
         from .surveys import TabulatedFunction
         pe = TabulatedFunction.coerce(survey.log_photo_error)
         p.photo_error = pe.describe(packer)
         dsat = survey.delta_saturation
         p.log_err_at_dsat = float(pe(dsat))
         p.err_bright = float(10 ** pe(dsat - 1))
+        for b in (_lib.BAND_G, _lib.BAND_R):       # saturated stars carry this constant error
+            with np.errstate(divide="ignore"):
+                tot = np.sqrt(np.float64(p.err_bright) ** 2 + np.float64(p.sys_error[b]) ** 2)
+                p.snr_bright_ok[b] = int(1.0 / tot >= SNR_MIN)
+        self._pack_maps()
         p.completeness = TabulatedFunction.coerce(survey.completeness).describe(packer)
         if perfect_galstarsep:
             det = getattr(survey, "efficiency_detection", None)
             if det is None:
                 raise ValueError("Efficiency function for type 'detection_efficiency' not loaded")
             p.detection = TabulatedFunction.coerce(det).describe(packer)
+
+    def _pack_maps(self):
+        """Interleave the three survey maps as [npix][4] = (ebv, maglim_g, maglim_r, 0): the
+        production kernel then gathers ONE 32-byte sector per star instead of three.  Only
+        when the three maps share one nside; ``packed_maps='auto'`` also wants the copy
+        (4/3 of the separate maps) to fit comfortably in free device memory."""
+        torch = _torch()
+        p = self.params
+        want = self._packed_maps
+        same = (p.band_present[0] and p.band_present[1] and not p.nest and
+                p.nside_maglim[0] == p.nside_ebv and p.nside_maglim[1] == p.nside_ebv)
+        if not want or not same:
+            return
+        npix = 12 * p.nside_ebv ** 2
+        if want == "auto":
+            free, _ = torch.cuda.mem_get_info(self.device)
+            if 32 * npix > 0.25 * free:
+                return
+        packed = torch.zeros((npix, 4), dtype=torch.float64, device=self.device)
+        for col, key in enumerate(("ebv", "g", "r")):
+            packed[:, col] = self._map_tensors[key]
+        self.packed_maps = packed
+        self.maps.packed = packed.data_ptr()
+        self.maps.nside_packed = p.nside_ebv
+
+    def hist_bin(self, name, values):
+        """Histogram bin of ``values`` exactly as the kernels compute it (fp32, two roundings;
+        -1 = outside or NaN)."""
+        k = _lib.HIST_NAMES.index(name)
+        lo = np.float32(self.params.hist_lo[k])
+        inv = np.float32(self.params.hist_inv_width[k])
+        with np.errstate(invalid="ignore", over="ignore"):
+            t = (np.asarray(values, dtype=np.float64).astype(np.float32) - lo) * inv
+            ok = (t >= 0) & (t < np.float32(_lib.HIST_BINS))
+            return np.where(ok, np.where(ok, t, 0).astype(np.int32), np.int32(-1)).astype(np.int32)
 
     def _describe_hist(self, hist):
         p = self.params
@@ -635,7 +718,41 @@ class StarEngine:
             t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64)).to(self.device)
         return t
 
-    def _draws_struct(self, draws, hold):
+    def _check_out(self, out, n, dtype, counters, host):
+        """Every output column must hold n elements of the launch's dtype, contiguous, on the
+        engine's device (pinned/CPU for the host variants): the kernel sees raw pointers."""
+        torch = _torch()
+        if dtype not in ("f64", "f32"):
+            raise ValueError("dtype must be 'f64' or 'f32'")
+        ft = torch.float64 if dtype == "f64" else torch.float32
+        want = {c: ft for c in COLUMNS_FLOAT}
+        want.update(flag_observed=torch.uint8, flag_perfect_galstarsep=torch.uint8, pix=torch.int64)
+        for name, t in out.items():
+            if t is None or name == "counters":
+                continue
+            if name == "draws":
+                if t.dtype != torch.float64 or t.numel() != _lib.N_DRAWS * n or not t.is_contiguous():
+                    raise ValueError("out['draws'] must be a contiguous float64 [8][n] tensor")
+            elif name in want:
+                if t.dtype != want[name]:
+                    raise ValueError(f"out['{name}'] has dtype {t.dtype}, expected {want[name]}")
+                if t.numel() < n or not t.is_contiguous():
+                    raise ValueError(f"out['{name}'] must be contiguous with at least {n} elements")
+            else:
+                continue
+            if host:
+                if t.device.type != "cpu":
+                    raise ValueError(f"out['{name}'] must be a host tensor")
+            elif t.device != self.device:
+                raise ValueError(f"out['{name}'] is on {t.device}, the engine on {self.device}")
+        cnt = counters if counters is not None else None
+        if cnt is not None:
+            if cnt.dtype != torch.int64 or cnt.numel() != _lib.COUNTERS_LEN or not cnt.is_contiguous():
+                raise ValueError(f"counters must be a contiguous int64[{_lib.COUNTERS_LEN}] tensor")
+            if (cnt.device.type != "cpu") if host else (cnt.device != self.device):
+                raise ValueError("counters live on the wrong device")
+
+    def _draws_struct(self, draws, hold, n=None):
         d = _lib.SSDraws()
         if not draws:
             return d
@@ -644,6 +761,9 @@ class StarEngine:
             for nm in names:
                 if nm in draws and draws[nm] is not None:
                     t = self._as_device_f64(draws[nm])
+                    if n is not None and t.numel() != n:
+                        raise ValueError(f"draws['{nm}'] has {t.numel()} elements, the launch "
+                                         f"covers {n} stars")
                     hold.append(t)
                     return t.data_ptr()
             return None
@@ -659,22 +779,28 @@ class StarEngine:
     def run(self, stages, n, out, catalog=None, draws=None, seed=0, offset=0, counters=None,
             dtype="f64"):
         """Launch ``stages`` for ``n`` stars into the column tensors of ``out``."""
-        if int(n) == 0:
+        n = int(n)
+        if n == 0:
             return out
         hold = []
         cat = _lib.SSCatalog()
+
+        def column(arr, what):
+            t = self._as_device_f64(arr)
+            if t.numel() != n:
+                raise ValueError(f"{what} has {t.numel()} elements, the launch covers {n} stars")
+            hold.append(t)
+            return t.data_ptr()
         if catalog:
             for name in ("phi1", "phi2", "dist", "ra", "dec"):
                 if catalog.get(name) is not None:
-                    t = self._as_device_f64(catalog[name])
-                    hold.append(t)
-                    setattr(cat, name, t.data_ptr())
+                    setattr(cat, name, column(catalog[name], f"catalog column '{name}'"))
             for band in ("g", "r"):
                 if catalog.get("mag_" + band) is not None:
-                    t = self._as_device_f64(catalog["mag_" + band])
-                    hold.append(t)
-                    cat.mag[_lib.BAND_INDEX[band]] = t.data_ptr()
-        d = self._draws_struct(draws, hold)
+                    cat.mag[_lib.BAND_INDEX[band]] = column(catalog["mag_" + band],
+                                                            f"catalog column 'mag_{band}'")
+        d = self._draws_struct(draws, hold, n)
+        self._check_out(out, n, dtype, counters, host=False)
         o = self._out_struct(out, counters, dtype)
         with _torch().cuda.device(self.device):
             rc = self.lib.ss_run(stages, C.byref(self.params), C.byref(self.tables),
@@ -764,6 +890,7 @@ class StarEngine:
         return out
 
     def generate_observe_host(self, n, out_host, workspace, chunk, seed=0, offset=0, dtype="f64"):
+        self._check_out(out_host, int(n), dtype, out_host.get("counters"), host=True)
         o = self._out_struct(out_host, out_host.get("counters"), dtype)
         with _torch().cuda.device(self.device):
             rc = self.lib.ss_generate_observe_host(
@@ -782,6 +909,12 @@ class StarEngine:
             if catalog_host.get("mag_" + band) is not None:
                 cat.mag[_lib.BAND_INDEX[band]] = catalog_host["mag_" + band].data_ptr()
         n = catalog_host["ra"].numel()
+        for name, t in catalog_host.items():
+            if t is not None and (t.device.type != "cpu" or t.dtype != _torch().float64
+                                  or t.numel() != n or not t.is_contiguous()):
+                raise ValueError(f"catalog_host['{name}'] must be a contiguous float64 host "
+                                 f"tensor of {n} elements")
+        self._check_out(out_host, n, dtype, out_host.get("counters"), host=True)
         o = self._out_struct(out_host, out_host.get("counters"), dtype)
         with _torch().cuda.device(self.device):
             rc = self.lib.ss_observe_host(
@@ -901,66 +1034,75 @@ def sample_inverse_cdf(vals, pdf, size, seed=None, u=None, device=None):
 
 def sample_loc_scale(loc, scale, size, normal, seed=None, draws=None, device=None):
     """``draw * scale + loc`` per star on the GPU (scipy ``rv.rvs`` semantics,
-    reference samplers.py:101-102), scalar or per-star loc/scale.
-
-    Implemented with the generate stage: an identity phi1 channel carries the
-    star index, the track channel applies the location/scale."""
+    reference samplers.py:101-102), scalar or per-star loc/scale -- one launch of
+    ``ss_loc_scale``; the draws are injected or the stars' own Philox draws."""
     torch = _torch()
     device = require_device(device)
+    lib = _lib.load()
     size = int(size)
-    loc_a = np.broadcast_to(np.asarray(loc, dtype=float), (size,))
-    scale_a = np.broadcast_to(np.asarray(scale, dtype=float), (size,))
+    loc_a, scale_a = np.asarray(loc, dtype=float), np.asarray(scale, dtype=float)
     if not np.all(scale_a >= 0):
         raise ValueError("Domain error in arguments. The `scale` parameter must be positive for "
                          "all distributions, and many distributions have restrictions on shape "
                          "parameters.")
     seed = _fresh_seed() if seed is None else seed
-    unit = _unit_engine(device, normal)
-    out = unit.allocate(size, ["phi2"])
-    d = None
+
+    def per_star(a):
+        if a.ndim == 0:
+            return None
+        return torch.from_numpy(np.ascontiguousarray(np.broadcast_to(a, (size,)))).to(device)
+    loc_t, scale_t = per_star(loc_a), per_star(scale_a)
+    draws_t = None
     if draws is not None:
-        d = {("z_phi2" if normal else "u_phi2"): draws}
-    unit.run(_lib.STAGE_GENERATE, size, out, None, d, seed)
-    z = out["phi2"]
-    res = z * torch.from_numpy(np.ascontiguousarray(scale_a)).to(device) \
-        + torch.from_numpy(np.ascontiguousarray(loc_a)).to(device)
-    return res.cpu().numpy()
+        draws_t = torch.from_numpy(np.ascontiguousarray(draws, dtype=np.float64)).to(device)
+        if draws_t.numel() != size:
+            raise ValueError(f"draws has {draws_t.numel()} elements, size is {size}")
+    out = torch.empty(size, dtype=torch.float64, device=device)
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    _small_call(lib.ss_loc_scale, device, int(bool(normal)), ptr(loc_t), ptr(scale_t),
+                float(loc_a) if loc_a.ndim == 0 else 0.0,
+                float(scale_a) if scale_a.ndim == 0 else 0.0, ptr(draws_t), out.data_ptr(),
+                size, 0, int(seed) & 0xFFFFFFFFFFFFFFFF)
+    return out.cpu().numpy()
 
 
-_UNIT = {}
-
-
-def _unit_engine(device, normal):
-    """Engine whose phi2 column is a raw standard draw (centre 0, scale 1)."""
-    key = (str(device), bool(normal))
-    if key in _UNIT:
-        return _UNIT[key]
+def noisy_magnitudes(mag_true, mag_err, z=None, seed=None, device=None):
+    """``StreamInjector.sample_measured_magnitudes`` on the GPU (``ss_noisy_magnitudes``):
+    float64 array, NaN where the noisy flux is not positive."""
     torch = _torch()
-    eng = StarEngine.__new__(StarEngine)
-    eng.lib = _lib.load()
-    eng.device = device
-    eng.params, eng.tables, eng.maps = _lib.SSParams(), _lib.SSTables(), _lib.SSMaps()
-    eng._keep = []
-    p = eng.params
-    p.density_kind = _lib.DENSITY_UNIFORM
-    p.density_lo, p.density_hi = 0.0, 1.0
-    for f, v in ((p.track_center, 0.0), (p.track_spread, 1.0)):
-        f.kind, f.xmin, f.xmax = _lib.FN_CONSTANT, -np.inf, np.inf
-        f.p[0] = v
-    if normal:
-        p.track_sampler = _lib.SAMPLER_GAUSSIAN
-    else:
-        # Uniform sampler on [c-s, c+s] with c=s=0.5 -> u*1 + 0
-        p.track_sampler = _lib.SAMPLER_UNIFORM
-        p.track_center.p[0] = 0.5
-        p.track_spread.p[0] = 0.5
-    blob = BlobPacker().finalize()
-    eng.blob = torch.from_numpy(blob).to(device)
-    eng.tables.blob, eng.tables.blob_bytes = eng.blob.data_ptr(), eng.blob.numel()
-    eng.set_frame(None)
-    eng._describe_hist(None)
-    _UNIT[key] = eng
-    return eng
+    device = require_device(device)
+    lib = _lib.load()
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(np.atleast_1d(a), dtype=np.float64)).to(device)
+    m, e = to(mag_true), to(mag_err)
+    if e.numel() != m.numel():
+        e = to(np.broadcast_to(np.asarray(mag_err, dtype=float), (m.numel(),)))
+    z_t = to(z) if z is not None else None
+    if z_t is not None and z_t.numel() != m.numel():
+        raise ValueError("z must have one entry per magnitude")
+    out = torch.empty_like(m)
+    seed = _fresh_seed() if seed is None else seed
+    _small_call(lib.ss_noisy_magnitudes, device, m.data_ptr(), e.data_ptr(),
+                z_t.data_ptr() if z_t is not None else None, out.data_ptr(), m.numel(), 0,
+                int(seed) & 0xFFFFFFFFFFFFFFFF)
+    return out.cpu().numpy()
+
+
+def bernoulli(prob, u=None, seed=None, device=None):
+    """``u <= prob`` per element on the GPU (``ss_bernoulli``); bool array."""
+    torch = _torch()
+    device = require_device(device)
+    lib = _lib.load()
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(np.atleast_1d(a), dtype=np.float64)).to(device)
+    pr = to(prob)
+    u_t = to(u) if u is not None else None
+    if u_t is not None and u_t.numel() != pr.numel():
+        raise ValueError("u must have one entry per probability")
+    out = torch.empty(pr.numel(), dtype=torch.uint8, device=device)
+    seed = _fresh_seed() if seed is None else seed
+    _small_call(lib.ss_bernoulli, device, pr.data_ptr(),
+                u_t.data_ptr() if u_t is not None else None, out.data_ptr(), pr.numel(), 0,
+                int(seed) & 0xFFFFFFFFFFFFFFFF)
+    return out.cpu().numpy().astype(bool)
 
 
 def _fresh_seed():

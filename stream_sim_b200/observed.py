@@ -350,36 +350,38 @@ class StreamInjector:
     # ------------------------------------------------------------------ pieces of inject
     def sample_measured_magnitudes(self, mag_true, mag_err, **kwargs):
         """Noisy magnitudes from flux-space Gaussian noise (reference :863-904);
-        "BAD_MAG" where the noisy flux is not positive.  Host arithmetic on the
-        GPU tensors via torch (this helper is not used by ``inject``, which has
-        the same arithmetic fused in the kernel)."""
-        import torch
-        from .engine import require_device
-        device = require_device(kwargs.pop("device", None))
+        "BAD_MAG" where the noisy flux is not positive.  One launch of
+        ``ss_noisy_magnitudes``; the normals come from ``rng`` (NumPy Generator: the
+        reference's stream), from ``z=`` or, by default, from the device's Philox stream
+        (``seed=``)."""
+        from .engine import noisy_magnitudes
+        z = kwargs.pop("z", None)
         rng = kwargs.pop("rng", None)
-        if rng is None:
-            rng = np.random.default_rng(kwargs.pop("seed", None))
-        m = torch.as_tensor(np.asarray(mag_true, dtype=float), device=device)
-        e = torch.as_tensor(np.asarray(mag_err, dtype=float), device=device)
-        z = torch.as_tensor(rng.standard_normal(m.shape), device=device)
-        flux = 3631.0 * 10 ** (-0.4 * m)
-        fobs = flux + (flux * e / 1.0857362) * z
-        mobs = (-2.5 * torch.log10(fobs / 3631.0)).cpu().numpy()
-        good = (fobs > 0.0).cpu().numpy()
+        if z is None and rng is not None:
+            z = rng.standard_normal(np.shape(mag_true))
+        mobs = noisy_magnitudes(np.asarray(mag_true, dtype=float), np.asarray(mag_err, dtype=float),
+                                z=z, seed=kwargs.pop("seed", None),
+                                device=kwargs.pop("device", None))
+        mobs = mobs.reshape(np.shape(mag_true))
+        good = ~np.isnan(mobs)
         return np.where(good, mobs, "BAD_MAG")
 
     def detect_flag(self, pix, mag=None, band="r", **kwargs):
         """Bernoulli detection against the survey completeness at ``pix``
-        (reference :906-959)."""
+        (reference :906-959): the efficiency getter and the trial (``ss_bernoulli``)
+        both run on the GPU; uniforms from ``rng`` / ``u=`` or the device's Philox
+        stream (``seed=``)."""
+        from .engine import bernoulli
+        u = kwargs.pop("u", None)
         rng = kwargs.pop("rng", None)
-        if rng is None:
-            rng = np.random.default_rng(kwargs.pop("seed", None))
+        if u is None and rng is not None:
+            u = rng.uniform(size=len(mag))
         maglim = self.survey.get_maglim(band, pixel=pix)
         if kwargs.get("perfect_galstarsep", False):
             compl = self.survey.get_detection_efficiency(band, mag, maglim)
         else:
             compl = self.survey.get_completeness(band, mag, maglim)
-        return rng.uniform(size=len(mag)) <= compl
+        return bernoulli(compl, u=u, seed=kwargs.pop("seed", None), device=kwargs.pop("device", None))
 
     def _save_injected_data(self, data, folder):
         if folder is None:
