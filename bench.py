@@ -214,7 +214,15 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------ GPU arm
-def build_engine(device, nside, survey=None, math="f64"):
+MATH_NOTE = {
+    "f64": "every value computed in double",
+    "fast": "same pixels, flags, positions and true magnitudes as f64 (all decisions in double); "
+            "magerr / mag_obs values from fp32 MUFU arithmetic with a double redo inside a guard "
+            "band: <= 1e-5 relative (north star bar for fp64 outputs)",
+}
+
+
+def build_engine(device, nside, survey=None, math="f64", fused=1):
     from helpers import stream_config
     from stream_sim_b200.engine import StarEngine
     from stream_sim_b200.frames import GreatCircleFrame
@@ -224,7 +232,7 @@ def build_engine(device, nside, survey=None, math="f64"):
     survey = Survey.synthetic(nside, nside, device=device) if survey is None else survey
     eng = StarEngine(stream=StreamModel(stream_config("pal5")), survey=survey,
                      frame=GreatCircleFrame.from_endpoints(*NOTEBOOK_ENDPOINTS), device=device,
-                     nside=nside, hist=True, math=math)
+                     nside=nside, hist=True, math=math, fused_kernel=bool(fused))
     return eng, survey
 
 
@@ -240,7 +248,7 @@ def run_gpu(args):
     device = torch.device("cuda", local)
     # host buffers of the end-to-end leg on the GPU's own NUMA node
     prev_affinity = ssd.bind_host_to_gpu(local)
-    eng, survey = build_engine(device, NSIDE, math=args.math)
+    eng, survey = build_engine(device, NSIDE, math=args.math, fused=args.fused)
     n = args.stars
     dtype = args.dtype
     out = eng.allocate(n, COLUMNS, dtype)
@@ -288,10 +296,11 @@ def run_gpu(args):
         raise SystemExit(f"counter check failed: n_total {summary['n_total']} (expected "
                          f"{expect_total}), n_observed {summary['n_observed']}")
 
-    # ---- supplementary: the mixed-precision kernel on the same workload (not the headline)
-    mixed = None
-    if args.mixed:
-        eng_m, _ = build_engine(device, NSIDE, survey=survey, math="mixed")
+    # ---- supplementary: the other arithmetic mode of the production kernel, same workload
+    other = None
+    if not args.no_other_math:
+        other_math = "fast" if args.math == "f64" else "f64"
+        eng_m, _ = build_engine(device, NSIDE, survey=survey, math=other_math, fused=args.fused)
         cm = eng_m.new_counters()
         for k in range(3):
             eng_m.generate_observe(n, seed=args.seed, offset=k * n, counters=cm, dtype=dtype, out=out)
@@ -303,10 +312,9 @@ def run_gpu(args):
                                    counters=cm, dtype=dtype, out=out)
         m1.record()
         barrier()
-        mixed_ms = ssd.max_over_ranks(m0.elapsed_time(m1), device) / args.steps
-        mixed = {"value": world * n / (mixed_ms * 1e-3), "unit": "stars/s", "ms_per_step": mixed_ms,
-                 "math": "fp32 Box-Muller/10^x/sqrt/log with fp64 fallback near thresholds; "
-                         "pix and flags identical to f64, mags ~1e-6 relative"}
+        other_ms = ssd.max_over_ranks(m0.elapsed_time(m1), device) / args.steps
+        other = {"math": other_math, "value": world * n / (other_ms * 1e-3), "unit": "stars/s",
+                 "ms_per_step": other_ms, "note": MATH_NOTE[other_math]}
         del eng_m
 
     # ---- end to end through the C ABI with HOST buffers (pinned), D2H inside
@@ -350,11 +358,12 @@ def run_gpu(args):
         "metric": "observed stars/sec", "value": value, "unit": "stars/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": dtype if args.math == "f64" else dtype + " storage, mixed f32/f64 math",
+        "dtype": dtype,
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "stars_per_step_per_gpu": n, "nside": NSIDE,
                    "stream": "config/pal5_config.yaml + synthetic isochrone",
                    "rng": "philox4x32-10 (device)", "seed": args.seed,
+                   "math": args.math, "math_note": MATH_NOTE[args.math],
                    "l2": "no per-star inputs; outputs (%.1f GB/step) exceed L2 and are "
                          "rewritten every step; map/table gathers are L2-resident by design"
                          % (n * bps / 1e9),
@@ -363,7 +372,10 @@ def run_gpu(args):
                    "observed_fraction": summary["n_observed"] / max(1, summary["n_total"])},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None if traffic is None else traffic * n,
-                     "peak_source": peak_src, "kernel": "k_stars<GENERATE|ROTATE|OBSERVE>",
+                     "traffic_source": "profiles/traffic.json (ncu capture of this kernel, bytes per "
+                                       "star x stars per launch; not measured in this run)",
+                     "peak_source": peak_src,
+                     "kernel": "k_fused" if args.fused else "k_stars<GENERATE|ROTATE|OBSERVE>",
                      "algorithmic_bytes_per_star": bps, "kernel_ms": kernel_ms},
         "e2e": {"value": e2e_value, "unit": "stars/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "stars_per_step_per_gpu": n_e2e,
@@ -372,9 +384,9 @@ def run_gpu(args):
         "gpu_launches": args.steps,
         "clocks": clocks,
     }
-    if mixed is not None:
-        mixed["roofline_frac"] = (mixed["value"] / world) * bps / 1e9 / peak
-        line["mixed_precision"] = mixed
+    if other is not None:
+        other["roofline_frac"] = (other["value"] / world) * bps / 1e9 / peak
+        line["other_math"] = other
     if world == 1 and not args.no_cpu:
         if prev_affinity is not None:
             os.sched_setaffinity(0, prev_affinity)      # the CPU arm gets every host core
@@ -422,11 +434,12 @@ def main():
     ap.add_argument("--seed", type=int, default=12345)
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--mixed", action="store_true",
-                    help="also time the mixed-precision kernel (supplementary line 'mixed_precision')")
-    ap.add_argument("--no-mixed", action="store_true", help="accepted for compatibility (default)")
-    ap.add_argument("--math", choices=("f64", "mixed"), default="f64",
-                    help="arithmetic of the main leg (default f64; 'mixed' is for profiling)")
+    ap.add_argument("--math", choices=("f64", "fast"), default="f64",
+                    help="arithmetic of the main leg (see MATH_NOTE)")
+    ap.add_argument("--no-other-math", action="store_true",
+                    help="skip the supplementary leg that times the other arithmetic mode")
+    ap.add_argument("--fused", type=int, default=1,
+                    help="1: production kernel k_fused (default); 0: the generic k_stars")
     ap.add_argument("--no-e2e", action="store_true",
                     help="profiling runs: shrink the end-to-end leg to a token size")
     args = ap.parse_args()

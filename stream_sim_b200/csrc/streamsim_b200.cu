@@ -16,6 +16,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <map>
+#include <utility>
+
 #include "device_math.cuh"
 
 #ifndef SS_BLOCK
@@ -660,6 +663,8 @@ k_fused(const __grid_constant__ KArgs a) {
   const double2* __restrict__ const grid_lut = reinterpret_cast<const double2*>(a.t.grid_lut);
   const double2* __restrict__ const iso_lut = reinterpret_cast<const double2*>(a.t.iso_lut);
   const uint32_t grid_lut_n = (uint32_t)p.grid_lut_n, iso_lut_n = (uint32_t)p.iso_lut_n;
+  const bool z_track = p.track_sampler == SS_SAMPLER_GAUSSIAN;
+  const bool z_dist = p.dist_sampler == SS_SAMPLER_GAUSSIAN;
 
   uint4 wp = make_uint4(0u, 0u, 0u, 0u);
   double2 eg = make_double2(0.0, 0.0), ei = make_double2(0.0, 0.0);
@@ -691,13 +696,18 @@ k_fused(const __grid_constant__ KArgs a) {
       if (k > 1) idx = step_scan(a.t.iso_thr, lo, k, u_mass, iso_lut_n);
       iso_row_eval(a.t.iso_rows, idx, u_mass, m1, m2);
     }
-    float zf_phi2, zf_dist;
-    ss::bm32f(wp.z, wp.w, zf_phi2, zf_dist);
-    if (!(row.s >= 0.0) || !(row.ds >= 0.0)) {                      // scipy: scale must be >= 0
-      if (want_cnt) atomicAdd(&s_cnt[SS_CNT_DOMAIN], (row.s >= 0.0 ? 0u : 1u) + (row.ds >= 0.0 ? 0u : 1u));
+    // the two track draws: normals (fp32 Box-Muller) or uniforms, per the samplers
+    double n_phi2, n_dist;
+    {
+      float zf0 = 0.0f, zf1 = 0.0f;
+      if (z_track || z_dist) ss::bm32f(wp.z, wp.w, zf0, zf1);
+      n_phi2 = z_track ? (double)zf0 : ss::u32(wp.z);
+      n_dist = z_dist ? (double)zf1 : ss::u32(wp.w);
     }
-    const double phi2 = __dadd_rn(__dmul_rn((double)zf_phi2, row.s), row.c);
-    const double dist = __dadd_rn(__dmul_rn((double)zf_dist, row.ds), row.dc);
+    unsigned c_dom = 0;
+    const double phi2 = track_draw(row.c, row.s, p.track_sampler, n_phi2, c_dom);
+    const double dist = track_draw(row.dc, row.ds, p.dist_sampler, n_dist, c_dom);
+    if (c_dom && want_cnt) atomicAdd(&s_cnt[SS_CNT_DOMAIN], c_dom);
     const double mag_g = __dadd_rn(m1, dist), mag_r = __dadd_rn(m2, dist);
     put<OutT>(a.o.phi1, i, row.x);
     put<OutT>(a.o.phi2, i, phi2);
@@ -765,7 +775,7 @@ k_fused(const __grid_constant__ KArgs a) {
     SS_COUNT(SS_CNT_OBSERVED, o.observed);
     if (p.perfect_galstarsep) SS_COUNT(SS_CNT_PERFECT, o.perfect);
 
-    if (i + stride < n && i + stride > i) prepare(i + stride);
+    if (i + stride < n) prepare(i + stride);                       // n <= 2^31: no wrap-around
   }
 
   if (want_cnt) {
@@ -947,20 +957,17 @@ int plan_launch(const DevInfo& d, int64_t blob_bytes, uint64_t n, int& smem, int
   return SS_OK;
 }
 
-// the opt-in dynamic shared-memory limit is a per-device, per-kernel attribute
+// the opt-in dynamic shared-memory limit is a per-device, per-kernel attribute: remember
+// the largest size configured for each (kernel, device)
 template <typename K>
 int launch_kernel(K kern, const KArgs& a, int smem, int grid, int block, cudaStream_t stream) {
-  static thread_local int configured_smem[64];
-  static thread_local bool init = false;
-  if (!init) {
-    for (int& v : configured_smem) v = -1;
-    init = true;
-  }
+  static thread_local std::map<std::pair<const void*, int>, int> configured;
   int dev = 0;
   SS_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || smem > configured_smem[dev]) {
+  int& have = configured.emplace(std::make_pair((const void*)kern, dev), -1).first->second;
+  if (smem > have) {
     SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    if (dev >= 0 && dev < 64) configured_smem[dev] = smem;
+    have = smem;
   }
   kern<<<grid, block, smem, stream>>>(a);
   SS_CUDA(cudaGetLastError());
@@ -978,7 +985,6 @@ bool fused_eligible(const KArgs& a, int smem) {
   const SSDraws& d = a.d;
   return p.fused_kernel && smem > 0 && p.density_kind == SS_DENSITY_GRID && !p.nest && p.has_dist &&
          p.has_iso && p.iso_direct && p.band_present[0] && p.band_present[1] &&
-         p.track_sampler == SS_SAMPLER_GAUSSIAN && p.dist_sampler == SS_SAMPLER_GAUSSIAN &&
          !d.u_phi1 && !d.u_mass && !d.n_phi2 && !d.n_dist && !d.z_flux[0] && !d.z_flux[1] &&
          !d.u_det && !d.u_det2 && !a.in.phi1 && !a.in.phi2 && !a.in.dist && !a.o.draws_out &&
          a.n <= (1ULL << 31);
@@ -1154,12 +1160,39 @@ int ss_launch_info(int64_t blob_bytes, uint64_t n, int32_t* smem_bytes, int32_t*
   return SS_OK;
 }
 
+static size_t elem_size(int32_t dtype);
+
 int ss_run(uint32_t stages, const SSParams* p, const SSTables* t, const SSMaps* m,
            const SSCatalog* in, const SSDraws* d, const SSOut* out, uint64_t n,
            uint64_t star_offset, uint64_t seed, void* stream) {
   if (n == 0) return SS_OK;   // nothing to do (empty arrays may legitimately be NULL)
   int rc = validate(stages, p, t, m, in, out);
   if (rc) return rc;
+  // The production kernel indexes stars with 32 bits inside a launch.  A longer free-running
+  // range is cut into 2^30-star launches: draws are keyed by the global index, so the result
+  // is the same bytes (columns advance with the range).
+  const uint64_t kSplit = 1ULL << 30;
+  static const SSDraws no_draws = {};
+  static const SSCatalog no_cat = {};
+  if (stages == (SS_STAGE_GENERATE | SS_STAGE_ROTATE | SS_STAGE_OBSERVE) && n > (1ULL << 31) &&
+      p->fused_kernel && (!d || !memcmp(d, &no_draws, sizeof(SSDraws))) &&
+      (!in || !memcmp(in, &no_cat, sizeof(SSCatalog))) && !out->draws_out) {
+    const size_t es = elem_size(out->dtype);
+    for (uint64_t lo = 0; lo < n; lo += kSplit) {
+      SSOut o = *out;
+      void** cols[11] = {&o.phi1, &o.phi2, &o.dist, &o.mag[0], &o.mag[1], &o.ra, &o.dec,
+                         &o.mag_obs[0], &o.mag_obs[1], &o.magerr[0], &o.magerr[1]};
+      for (void** c : cols)
+        if (*c) *c = (char*)*c + lo * es;
+      if (o.flag_observed) o.flag_observed += lo;
+      if (o.flag_perfect) o.flag_perfect += lo;
+      if (o.pix) o.pix += lo;
+      const uint64_t cn = (n - lo < kSplit) ? n - lo : kSplit;
+      if ((rc = ss_run(stages, p, t, m, nullptr, nullptr, &o, cn, star_offset + lo, seed, stream)))
+        return rc;
+    }
+    return SS_OK;
+  }
   DevInfo dev;
   if ((rc = device_info(dev))) return rc;
   KArgs a;

@@ -74,7 +74,12 @@ def reduce_counters(counters):
     steps by the world size at every further reduction."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(counters, op=dist.ReduceOp.SUM)
+        if counters.is_cuda and dist.get_backend() == "gloo":
+            host = counters.cpu()                 # gloo reduces on the host
+            dist.all_reduce(host, op=dist.ReduceOp.SUM)
+            counters.copy_(host)
+        else:
+            dist.all_reduce(counters, op=dist.ReduceOp.SUM)
     return counters
 
 

@@ -5,15 +5,34 @@ import streamsim_oracle as oracle
 from stream_sim_b200 import synthetic as syn
 
 
-def oracle_survey(compl_band="r", first=-10.4, nside_maglim=128, nside_ebv=512):
+class LazyMap:
+    """A synthetic HEALPix map evaluated only at the pixels asked for (the maps are closed-form
+    hashes of the pixel index): lets the oracle look up nside-4096 maps without building
+    200-million-pixel arrays on the host.  Supports what the oracle uses: len() and
+    indexing with an integer array."""
+
+    def __init__(self, kind, nside):
+        self.kind, self.nside = kind, nside
+
+    def __len__(self):
+        return 12 * self.nside * self.nside
+
+    def __getitem__(self, pix):
+        s_val, s_hole = syn._SALT[self.kind]
+        pix = np.asarray(pix, dtype=np.uint64)
+        return syn._map_from_hash(syn._mix_np(pix, s_val), syn._mix_np(pix, s_hole), self.kind, np)
+
+
+def oracle_survey(compl_band="r", first=-10.4, nside_maglim=128, nside_ebv=512, lazy=False):
     """Survey dict for the oracle, from the same synthetic inputs as Survey.synthetic."""
     props = syn.LSST_PROPS
     eff = syn.efficiency_csv_columns(first=first)
     err = syn.photo_error_csv_columns(first=first)
     dsat = props["delta_saturation"]
-    return dict(ebv_map=syn.healpix_map("ebv", nside_ebv),
-                maglim_maps=dict(g=syn.healpix_map("maglim_g", nside_maglim),
-                                 r=syn.healpix_map("maglim_r", nside_maglim)),
+    mk = LazyMap if lazy else syn.healpix_map
+    return dict(ebv_map=mk("ebv", nside_ebv),
+                maglim_maps=dict(g=mk("maglim_g", nside_maglim),
+                                 r=mk("maglim_r", nside_maglim)),
                 coeff_extinc=props["coeff_extinc"], saturation=props["saturation"],
                 sys_error=props["sys_error"], delta_saturation=dsat,
                 completeness_band=compl_band,
@@ -25,8 +44,22 @@ def oracle_survey(compl_band="r", first=-10.4, nside_maglim=128, nside_ebv=512):
 
 
 def stream_config(name):
-    """Stream sections used by tests/bench: reference configs + synthetic isochrone."""
+    """Stream sections used by tests/bench: reference configs + synthetic isochrone.
+    ``atlas_spline`` / ``phoenix_spline``: the Patrick et al. (2022) spline streams with
+    their distance-modulus splines (the configs of the golden generate fixtures)."""
     from stream_sim_b200.utils import parse_config
+    if name in ("atlas_spline", "phoenix_spline"):
+        f = "./data/patrick_2022_splines.csv"
+        sn = name.split("_")[0]
+        spl = lambda t: dict(type="FileCubicSplineInterpolation", filename=f, spline_type=t,
+                             stream_name=sn)
+        return dict(density=dict(type="FileLinearDensityCubicSplineInterpolation", filename=f,
+                                 stream_name=sn),
+                    track=dict(center=spl("center"), spread=spl("spread"), sampler="Gaussian"),
+                    distance_modulus=dict(center=spl("dist_mod"),
+                                          spread=dict(type="Constant", value=0.05),
+                                          sampler="Gaussian"),
+                    isochrone=dict(name="synthetic"))
     cfg = parse_config(f"config/{name}_config.yaml")["stream"]
     cfg["isochrone"] = dict(name="synthetic")
     return cfg

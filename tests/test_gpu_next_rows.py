@@ -296,3 +296,48 @@ def test_cli_driver(tmp_path):
     df = pd.read_csv(out)
     assert len(df) == 110000 and set(df["flag"]) == {0, 1} and (df["flag"] == 1).sum() == 10000
     assert df["phi1"].between(-10, 10).all()
+
+
+def test_standalone_noise_and_detection_entry_points(survey):
+    """StreamInjector.sample_measured_magnitudes / detect_flag (reference observed.py:863-959)
+    run on the GPU (ss_noisy_magnitudes, ss_efficiency + ss_bernoulli): with the reference's
+    own draws (a NumPy Generator) they equal the oracle's NumPy arithmetic -- BAD_MAG pattern
+    and flags exact, magnitudes to 1e-12 -- and free-running they use the stars' own Philox
+    draws."""
+    from stream_sim_b200.observed import StreamInjector
+    inj = StreamInjector(survey)
+    n = 200000
+    rng = np.random.default_rng(4)
+    mag = rng.uniform(17.0, 29.0, n)
+    mag[:3] = [np.nan, 250.0, -250.0]
+    err = 10 ** rng.uniform(-3, 0.7, n)              # up to 5 mag: some fluxes go negative
+    z = np.random.default_rng(99).standard_normal(n)
+    got = inj.sample_measured_magnitudes(mag, err, rng=np.random.default_rng(99))
+    with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+        flux = 3631.0 * 10 ** (-0.4 * mag)
+        fobs = flux + (flux * err / 1.0857362) * z
+        ref = np.where(fobs > 0.0, -2.5 * np.log10(fobs / 3631.0), np.nan)
+    bad = np.array([isinstance(v, str) and v == "BAD_MAG" for v in got])
+    assert np.array_equal(bad, np.isnan(ref)) and 100 < bad.sum() < n / 2
+    assert_close(np.array([float(v) for v in got[~bad]]), ref[~bad], 1e-12, 1e-12, "noisy magnitudes")
+    # free-running: the stars' own z_r (fp32 Box-Muller of Philox OBS block)
+    d = oracle.device_draws(5, 0, n)
+    free = inj.sample_measured_magnitudes(mag, err, seed=5)
+    with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+        fobs = flux + (flux * err / 1.0857362) * d["z_r"]
+    ok = (free != "BAD_MAG") & (fobs > 1e-3 * flux)
+    assert ok.sum() > n / 2
+    assert_close(np.array([float(v) for v in free[ok]]), -2.5 * np.log10(fobs[ok] / 3631.0), 0, 5e-3,
+                 "free-running noisy magnitudes")
+    # detect_flag
+    sv = oracle_survey()
+    pix = rng.integers(0, 12 * 128 * 128, n)
+    magr = rng.uniform(15.5, 28.0, n)
+    u = np.random.default_rng(7).uniform(size=n)
+    for perfect, table in ((False, "completeness"), (True, "efficiency_detection")):
+        flag = inj.detect_flag(pix, magr, "r", rng=np.random.default_rng(7), perfect_galstarsep=perfect)
+        ref_flag = u <= oracle.get_efficiency(sv, "r", magr, sv["maglim_maps"]["r"][pix], table)
+        assert flag.dtype == bool and np.array_equal(flag, ref_flag), table
+    free_flag = inj.detect_flag(pix, magr, "r", seed=5)
+    assert np.array_equal(free_flag, d["u_det"] <= oracle.get_efficiency(
+        sv, "r", magr, sv["maglim_maps"]["r"][pix]))

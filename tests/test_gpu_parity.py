@@ -102,23 +102,25 @@ def test_ang2pix_matches_oracle_all_branches(torch_cuda):
 
 
 # ------------------------------------------------------------------ fused path
-def _fused_engine(cfg_name="pal5", compl_band="r", **kw):
+def _fused_engine(cfg_name="pal5", compl_band="r", nsides=(128, 512), **kw):
     from stream_sim_b200.engine import StarEngine
     from stream_sim_b200.frames import GreatCircleFrame
     from stream_sim_b200.model import StreamModel
     from stream_sim_b200.surveys import Survey
     from stream_sim_b200.synthetic import NOTEBOOK_ENDPOINTS
-    sv = Survey.synthetic(128, 512, completeness_band=compl_band)
+    sv = Survey.synthetic(*nsides, completeness_band=compl_band,
+                          **(dict(device="cuda") if max(nsides) >= 2048 else {}))
     frame = GreatCircleFrame.from_endpoints(*NOTEBOOK_ENDPOINTS)
     model = StreamModel(stream_config(cfg_name))
     return StarEngine(stream=model, survey=sv, frame=frame, **kw), frame
 
 
-def _oracle_fused(cfg_name, draws, compl_band="r", **kw):
+def _oracle_fused(cfg_name, draws, compl_band="r", nsides=(128, 512), **kw):
     from stream_sim_b200.synthetic import NOTEBOOK_ENDPOINTS, isochrone_table
     R = oracle.frame_from_endpoints(*NOTEBOOK_ENDPOINTS[0], *NOTEBOOK_ENDPOINTS[1])
-    return oracle.generate_observe(stream_config(cfg_name), isochrone_table(), R,
-                                   oracle_survey(compl_band), draws, **kw)
+    sv = oracle_survey(compl_band, nside_maglim=nsides[0], nside_ebv=nsides[1],
+                       lazy=max(nsides) >= 2048)
+    return oracle.generate_observe(stream_config(cfg_name), isochrone_table(), R, sv, draws, **kw)
 
 
 def _check_draws_against_oracle(used, seed, offset, n):
@@ -132,17 +134,37 @@ def _check_draws_against_oracle(used, seed, offset, n):
     return ref
 
 
-@pytest.mark.parametrize("cfg_name,grid_table", [("toy1", True), ("pal5", True), ("pal5", False)])
+GRID_CONFIGS = ("pal5", "atlas_spline", "phoenix_spline")   # inverse-CDF densities
+
+
+def _assert_same_bytes(torch, a, b, keys=None):
+    for k in (keys or a.keys()):
+        assert torch.equal(a[k].view(torch.uint8), b[k].view(torch.uint8)), k
+
+
+def _check_fast_against_f64(torch, fast, exact):
+    """SS_MATH_FAST: every decision and every position / true magnitude identical to the
+    double path, magerr and mag_obs within 1e-5 relative (the north star's fp64 bar)."""
+    _assert_same_bytes(torch, fast, exact, [k for k in exact if k in (
+        "pix", "flag_observed", "flag_perfect_galstarsep", "phi1", "phi2", "dist", "ra", "dec",
+        "mag_g", "mag_r")])
+    for k in ("mag_g_obs", "mag_r_obs", "magerr_g", "magerr_r"):
+        assert_close(fast[k].cpu().numpy(), exact[k].cpu().numpy(), 1e-5, 0, k)
+
+
+@pytest.mark.parametrize("cfg_name,grid_table", [("toy1", True), ("pal5", True), ("pal5", False),
+                                                 ("atlas_spline", True), ("phoenix_spline", True)])
 def test_fused_free_running_matches_oracle(torch_cuda, cfg_name, grid_table):
     """Free-running (Philox on the device) fused generate->rotate->observe equals the
     oracle fed with the draws the kernel used (exported through SSOut.draws_out, and
     themselves checked against the oracle's Philox derivation): pixel indices and
-    flags bit-exact, everything else to 1e-9.  The production (LEAN) instantiation,
-    which cannot export draws, must produce the very same bytes."""
+    flags bit-exact, everything else to 1e-9.  The production kernel (k_fused), which
+    cannot export draws, must produce the very same bytes as the generic kernel, with and
+    without the packed survey maps; its SS_MATH_FAST variant the same decisions."""
     n, seed, offset = 1 << 18, 12345, 1000
     eng, _ = _fused_engine(cfg_name, perfect_galstarsep=True, grid_table=grid_table)
     from stream_sim_b200 import _lib
-    assert (eng.params.density_kind == _lib.DENSITY_GRID) == (grid_table and cfg_name == "pal5")
+    assert (eng.params.density_kind == _lib.DENSITY_GRID) == (grid_table and cfg_name in GRID_CONFIGS)
     cnt = eng.new_counters()
     out = eng.generate_observe(n, seed=seed, offset=offset, counters=cnt, pix=True,
                                export_draws=True)
@@ -153,8 +175,14 @@ def test_fused_free_running_matches_oracle(torch_cuda, cfg_name, grid_table):
         assert np.abs(draws["z_phi2"] - odraws["z_phi2"]).max() < 5e-6
         assert np.array_equal(draws["u_dist"], odraws["u_dist"])
     lean = eng.generate_observe(n, seed=seed, offset=offset, pix=True)
-    for k, v in lean.items():
-        assert torch_cuda.equal(v.view(torch_cuda.uint8), out[k].view(torch_cuda.uint8)), k
+    _assert_same_bytes(torch_cuda, lean, out, lean.keys())
+    if eng.params.density_kind == _lib.DENSITY_GRID:
+        # (maps of different nside: the production kernel gathers the three maps separately)
+        assert not eng.maps.packed
+        generic, _ = _fused_engine(cfg_name, perfect_galstarsep=True, fused_kernel=False)
+        _assert_same_bytes(torch_cuda, generic.generate_observe(n, seed=seed, offset=offset, pix=True), lean)
+        fast, _ = _fused_engine(cfg_name, perfect_galstarsep=True, math="fast")
+        _check_fast_against_f64(torch_cuda, fast.generate_observe(n, seed=seed, offset=offset, pix=True), lean)
     ref = _oracle_fused(cfg_name, draws, perfect_galstarsep=True)
     assert np.array_equal(got["phi1"], ref["phi1"])
     assert np.array_equal(got["pix"], ref["pix"]), "pixel indices"
@@ -217,41 +245,65 @@ def test_fp32_output_mode(torch_cuda):
         assert_close(b[k].cpu().numpy().astype(float), a[k].cpu().numpy(), 1e-6, 1e-6, k)
 
 
-def test_mixed_precision_mode(torch_cuda):
-    """SS_MATH_MIXED: fp32 transcendentals with double fallback near decision
-    thresholds.  Under injected draws pixel indices and both flags are identical to
-    the fp64 path (hence to the reference), positions are untouched, magnitudes and
-    errors agree to 1e-5 relative (north-star bar for fp64 outputs)."""
+def test_fast_math_mode(torch_cuda):
+    """SS_MATH_FAST under injected draws (the generic kernel) against the oracle: pixel
+    indices and both flags bit-exact, positions and true magnitudes 1e-9, noisy magnitudes
+    and errors 1e-5 relative (the north star's bar for fp64 outputs); and the production
+    kernel free-running: same decisions as its double twin, star by star."""
     n, seed = 1 << 20, 4242
     exact, _ = _fused_engine("pal5", perfect_galstarsep=True)
-    mixed, _ = _fused_engine("pal5", perfect_galstarsep=True, math="mixed")
+    fast, _ = _fused_engine("pal5", perfect_galstarsep=True, math="fast")
     d = oracle.device_draws(seed, 0, n)
     inj = {k: d[k] for k in ("u_phi1", "z_phi2", "u_dist", "u_mass", "z_r", "z_g", "u_det", "u_det2")}
     a = exact.generate_observe(n, draws=inj, pix=True)
-    b = mixed.generate_observe(n, draws=inj, pix=True)
-    for k in ("pix", "flag_observed", "flag_perfect_galstarsep", "phi1", "phi2", "dist", "ra", "dec",
-              "mag_g", "mag_r"):
-        assert torch_cuda.equal(a[k].view(torch_cuda.uint8), b[k].view(torch_cuda.uint8)), k
-    for k in ("mag_g_obs", "mag_r_obs", "magerr_g", "magerr_r"):
-        assert_close(b[k].cpu().numpy(), a[k].cpu().numpy(), 1e-5, 0, k)
+    b = fast.generate_observe(n, draws=inj, pix=True)
+    _check_fast_against_f64(torch_cuda, b, a)
     ref = _oracle_fused("pal5", d, perfect_galstarsep=True)
     assert np.array_equal(b["pix"].cpu().numpy(), ref["pix"])
-    assert np.array_equal(b["flag_observed"].cpu().numpy().astype(bool), ref["flag_observed"])
-    # free-running (its own fp32 Box-Muller): same distributions
-    fa = exact.generate_observe(n, seed=seed)
-    fb = mixed.generate_observe(n, seed=seed)
-    pa, pb = float(fa["flag_observed"].float().mean()), float(fb["flag_observed"].float().mean())
-    assert abs(pa - pb) < 5 * np.sqrt(pa * (1 - pa) / n) + 1e-4
-    assert torch_cuda.equal(fa["phi1"], fb["phi1"])
-    for k in ("phi2", "mag_g_obs", "magerr_r"):
-        x, y = fa[k].cpu().numpy(), fb[k].cpu().numpy()
-        ok = ~(np.isnan(x) | np.isnan(y))
-        # same uniforms behind both: per-star values agree to fp32 round-off of the normals
-        assert np.median(np.abs(x[ok] - y[ok])) < 1e-5, k
-        assert np.quantile(np.abs(x[ok] - y[ok]), 0.99) < 1e-4, k
-        if k != "magerr_r":          # magerr has point masses (e.g. 10.000001): no KS
-            dks, crit = _ks(x[~np.isnan(x)][:200000], np.sort(y[~np.isnan(y)][:200000]))
-            assert dks < crit, k
+    for flag in ("flag_observed", "flag_perfect_galstarsep"):
+        assert np.array_equal(b[flag].cpu().numpy().astype(bool), ref[flag]), flag
+    for k in ("mag_g_obs", "mag_r_obs", "magerr_g", "magerr_r"):
+        assert_close(b[k].cpu().numpy(), ref[k], 1e-5, 0, k)
+    # free-running, production kernel, counters included
+    ca, cb = exact.new_counters(), fast.new_counters()
+    fa = exact.generate_observe(n, seed=seed, counters=ca, pix=True)
+    fb = fast.generate_observe(n, seed=seed, counters=cb, pix=True)
+    _check_fast_against_f64(torch_cuda, fb, fa)
+    assert torch_cuda.equal(ca, cb)
+    # the observe-only entry in fast mode
+    cat = {k: fa[k] for k in ("ra", "dec", "mag_g", "mag_r")}
+    oa, ob = exact.observe(cat, seed=seed), fast.observe(cat, seed=seed)
+    assert torch_cuda.equal(oa["flag_observed"], ob["flag_observed"])
+    assert_close(ob["mag_r_obs"].cpu().numpy(), oa["mag_r_obs"].cpu().numpy(), 1e-5, 0, "mag_r_obs")
+
+
+def test_lsst_configuration_star_by_star(torch_cuda):
+    """BASELINE config 4 as configured: nside-4096 depth and E(B-V) maps (built on the
+    device; the oracle evaluates the same closed-form maps at the pixels it needs), 2^22
+    stars, fused path against the oracle star by star -- pixels and flags bit-exact, the ten
+    float columns to 1e-9 -- and the production kernel (packed maps: one 32-byte record per
+    pixel) byte-equal to the generic kernel on separate maps."""
+    n, seed = 1 << 22, 777
+    eng, _ = _fused_engine("pal5", nsides=(4096, 4096), perfect_galstarsep=True)
+    assert eng.maps.packed and eng.maps.nside_packed == 4096
+    out = eng.generate_observe(n, seed=seed, pix=True, export_draws=True)      # generic kernel
+    prod = eng.generate_observe(n, seed=seed, pix=True)                        # k_fused, packed
+    _assert_same_bytes(torch_cuda, prod, out, prod.keys())
+    plain, _ = _fused_engine("pal5", nsides=(4096, 4096), perfect_galstarsep=True, packed_maps=False)
+    assert not plain.maps.packed
+    _assert_same_bytes(torch_cuda, plain.generate_observe(n, seed=seed, pix=True), prod)
+    del plain
+    got = {k: v.cpu().numpy() for k, v in out.items()}
+    draws = eng.exported_draws(out)
+    _check_draws_against_oracle(draws, seed, 0, n)
+    ref = _oracle_fused("pal5", draws, nsides=(4096, 4096), perfect_galstarsep=True)
+    assert np.array_equal(got["pix"], ref["pix"]), "pixel indices"
+    assert np.array_equal(got["flag_observed"].astype(bool), ref["flag_observed"])
+    assert np.array_equal(got["flag_perfect_galstarsep"].astype(bool), ref["flag_perfect_galstarsep"])
+    for k in ("phi2", "dist", "mag_g", "mag_r", "ra", "dec", "mag_g_obs", "mag_r_obs",
+              "magerr_g", "magerr_r"):
+        assert_close(got[k], ref[k], RTOL, 1e-9, k)
+    assert 0.15 < ref["flag_observed"].mean() < 0.3 and np.isnan(ref["magerr_r"]).mean() > 0.01
 
 
 def test_host_buffer_entry_equals_device_entry(torch_cuda):
@@ -294,10 +346,19 @@ def test_summary_only_mode_equals_full_run(torch_cuda):
     for name in ("phi1", "phi2", "dist", "mag_g", "g_minus_r"):
         assert 0 < s["hist_" + name].sum() <= n
     assert s["hist_phi1"].sum() == n          # pal5 phi1 lies inside the default range
-    # histogram of phi1 against numpy
+    # the five histograms against their definition (fp32 bins, SSParams.hist_*) on the columns
+    cols = {k: out[k].cpu().numpy() for k in ("phi1", "phi2", "dist", "mag_g", "mag_r")}
+    cols["g_minus_r"] = cols["mag_g"] - cols["mag_r"]
+    for name in ("phi1", "phi2", "dist", "mag_g", "g_minus_r"):
+        bins = eng.hist_bin(name, cols[name])
+        assert np.array_equal(s["hist_" + name], np.bincount(bins[bins >= 0], minlength=256)), name
+    # ... which is the plain histogram up to fp32 rounding at the bin edges
     lo, hi = eng.hist_ranges["phi1"]
-    ref = np.histogram(out["phi1"].cpu().numpy(), bins=256, range=(lo, hi))[0]
-    assert np.abs(s["hist_phi1"] - ref).sum() <= 4     # edge rounding only
+    ref = np.histogram(cols["phi1"], bins=256, range=(lo, hi))[0]
+    assert np.abs(s["hist_phi1"] - ref).sum() <= 1e-4 * n
+    # and the generic kernel fills the same histograms
+    generic, _ = _fused_engine("pal5", hist=True, fused_kernel=False)
+    assert torch_cuda.equal(generic.run_summary(n, seed=8, chunk=500000), full)
 
 
 def test_full_size_properties(torch_cuda):

@@ -597,3 +597,16 @@ def test_shard_ranges_cover_exactly():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert all(hi >= lo for lo, hi in spans)
+
+
+def test_snr_threshold_on_the_log_error():
+    """The SNR cut decided on log10(statistical error): the host threshold reproduces the
+    reference arithmetic 1/sqrt((10**x)**2 + sys**2) >= 5 on both sides of it."""
+    from stream_sim_b200.engine import snr_loge_threshold
+    for sys_err in (0.0, 0.005, 0.03, 0.15):
+        x = snr_loge_threshold(sys_err)
+        probe = x + np.array([-1e-3, -1e-9, -1e-13, 0.0]) 
+        above = x + np.array([1e-13, 1e-9, 1e-3])
+        ok = lambda v: 1.0 / np.sqrt((10 ** v) ** 2 + sys_err ** 2) >= 5.0
+        assert ok(probe).all() and not ok(above).any(), sys_err
+    assert np.isnan(snr_loge_threshold(0.3))          # sys error alone fails the cut
