@@ -90,7 +90,7 @@ extern "C" {
 /* Philox4x32-10 draw blocks: counter = (star_lo, star_hi, block, 0),
  * key = (seed_lo, seed_hi), output words (w0,w1,w2,w3).  Two blocks per star:
  *   U32(a)   = a * 2^-32                       (uniform in [0,1), exact in double)
- *   BM32(a,b): fp32 Box-Muller, radius from y = (a+0.5)/2^32, angle 2*pi*b/2^32
+ *   BM32(a,b): fp32 Box-Muller, radius sqrt(-2 ln y), y = (~a + 0.5)/2^32, angle 2*pi*b/2^32
  *   block 0 (POS): u_phi1 = U32(w0), u_mass = U32(w1),
  *                  (z_phi2, z_dist) = BM32(w2,w3)   [Uniform samplers: U32(w2), U32(w3)]
  *   block 1 (OBS): (z_r, z_g) = BM32(w0,w1) flux noise,

@@ -83,17 +83,13 @@ def _u32(a):
 
 
 def bm32(wa, wb):
-    """The device's fp32 Box-Muller from two 32-bit words, emulated with NumPy float32.
-    NOT bit-identical to the CUDA intrinsics (agrees to ~1e-6): tests that need the exact
-    normals read them back from the kernel (SSOut.draws_out) instead."""
+    """The device's fp32 Box-Muller from two 32-bit words, emulated with NumPy float32:
+    radius from y = (~wa + 0.5) / 2^32, angle 2 pi wb / 2^32.  NOT bit-identical to the CUDA
+    intrinsics (MUFU log2 / sqrt / sin / cos: agrees to ~1e-6, less near z = 0): tests that
+    need the exact normals read them back from the kernel (SSOut.draws_out) instead."""
     f = np.float32
-    k = f(2.3283064365386963e-10)
-    y = (wa.astype(f) + f(0.5)) * k
-    c1 = ((~wa).astype(f) + f(0.5)) * k
-    series = -c1 * (f(1) + c1 * (f(0.5) + c1 * (f(0.33333334) + c1 * f(0.25))))
-    with np.errstate(divide="ignore"):
-        l = np.where(c1 < f(0.03), series, np.log(y)).astype(f)
-    r = np.sqrt(f(-2) * l)
+    y = ((~wa).astype(f) + f(0.5)) * f(2.3283064365386963e-10)
+    r = np.sqrt(f(-1.3862943611198906) * np.log2(y).astype(f))
     ang = wb.astype(np.float64) * 4.6566128730773926e-10
     return ((r * np.cos(np.pi * ang).astype(f)).astype(np.float64),
             (r * np.sin(np.pi * ang).astype(f)).astype(np.float64))

@@ -1,0 +1,20 @@
+#!/bin/bash
+# Quick perf comparison: in-tree library + every build/variants/*.so, both math modes.
+tag=${1:-v}
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_parity.py -q -k "fused_free_running or fast_math or lsst_configuration or summary_only or shard" > gpurun_out/${tag}_pytest.log 2>&1; tail -3 gpurun_out/${tag}_pytest.log
+timeout 300 python bench.py --no-cpu --no-e2e --steps 10 > gpurun_out/${tag}_intree.json 2> gpurun_out/${tag}_intree.err
+for lib in build/variants/*.so; do
+  name=$(basename $lib .so)
+  STREAMSIM_B200_LIB=$PWD/$lib timeout 300 python bench.py --no-cpu --no-e2e --steps 10 > gpurun_out/${tag}_${name}.json 2> gpurun_out/${tag}_${name}.err
+done
+python - <<PY
+import glob, json
+for f in sorted(glob.glob("gpurun_out/${tag}_*.json")):
+    try:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+        o = d.get("other_math", {})
+        print("%-50s %s %.4g (frac %.4f)   %s %.4g" % (f, d["config"]["math"], d["value"], d["roofline"]["frac"], o.get("math"), o.get("value", 0)))
+    except Exception as e:
+        print(f, "unreadable", e)
+PY

@@ -31,6 +31,28 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 
+// The same ten rounds with the key schedule precomputed by the host (rk[2r], rk[2r+1] =
+// key + r * Weyl constants): as launch constants the round keys are constant-bank operands
+// of the XORs, so a round is two wide multiplies and two three-input XORs.
+struct PhiloxKeys {
+  uint32_t rk[20];
+};
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys& K) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ K.rk[2 * r], lo1, hi0 ^ c.w ^ K.rk[2 * r + 1], lo0);
+  }
+  return c;
+}
+
+__device__ __forceinline__ uint4 philox_block(unsigned long long star, uint32_t block,
+                                              const PhiloxKeys& K) {
+  return philox4x32_10(make_uint4((uint32_t)star, (uint32_t)(star >> 32), block, 0u), K);
+}
+
 // two 32-bit words -> double in [0,1) with 52 random bits: the bits become the
 // mantissa of a double in [1,2), minus 1 (two integer ops and one DADD; no I2F)
 __device__ __forceinline__ double u52(uint32_t a, uint32_t b) {
@@ -54,22 +76,17 @@ __device__ __forceinline__ double u32(uint32_t w) { return word_to_double(w) * (
 
 // Box-Muller from two 32-bit words, evaluated in fp32 (like cuRAND's curand_normal): the
 // draw is a random number, not a quantity with a parity requirement, and everything
-// computed *from* it downstream stays in double.  y = (wa+0.5)/2^32 in (0,1) feeds the
-// radius; for y close to 1 the complement (~wa+0.5)/2^32 = 1-y is exact and a short
-// series replaces log(y), which would lose relative accuracy there.  |z| <= 6.7.
+// computed *from* it downstream stays in double.  Radius from y = (~wa + 0.5) / 2^32 in
+// (0, 1): small y (the tail) keeps full relative precision in fp32; |z| <= 6.7.
 __device__ __forceinline__ void bm32f(uint32_t wa, uint32_t wb, float& z0, float& z1) {
-  const float y = ((float)wa + 0.5f) * 2.3283064365386963e-10f;
-  const float c1 = ((float)(~wa) + 0.5f) * 2.3283064365386963e-10f;
-  const float l_series = -c1 * (1.0f + c1 * (0.5f + c1 * (0.33333334f + c1 * 0.25f)));
-  const float l = (c1 < 0.03f) ? l_series : __logf(y);
+  const float y = ((float)(~wa) + 0.5f) * 2.3283064365386963e-10f;
   float r;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * l));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * __log2f(y)));
   // angle = 2 pi wb / 2^32, taken modulo 2 pi into [-pi, pi) (wb read as a signed word) where
   // the MUFU sine / cosine are good to 5e-7 absolute
   const float ang = (float)(int)wb * 4.6566128730773926e-10f * 3.14159265358979f;
-  const float s = __sinf(ang), c = __cosf(ang);
-  z0 = r * c;
-  z1 = r * s;
+  z0 = r * __cosf(ang);
+  z1 = r * __sinf(ang);
 }
 
 __device__ __forceinline__ void bm32(uint32_t wa, uint32_t wb, double& z0, double& z1) {
@@ -209,7 +226,8 @@ __device__ __forceinline__ double exp10_fast(double x) {
 // atan(q) = atan(i/8) + atan((q - c)/(1 + q c)), |r| <= 1/16, one division.
 __device__ __forceinline__ double atan2_nb(double y, double x) {
   const double ax = fabs(x), ay = fabs(y);
-  const double mx = fmax(ax, ay), mn = fmin(ax, ay);
+  const bool steep = ay > ax;
+  const double mx = steep ? ay : ax, mn = steep ? ax : ay;
   double r0;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(mx));
   const double t = fma(mn * r0, 8.0, kNum[10]);
@@ -223,10 +241,16 @@ __device__ __forceinline__ double atan2_nb(double y, double x) {
   pe = fma(pe, r4, kAtanC[0]); po = fma(po, r4, kAtanC[1]);
   const double p = fma(po, r2, pe);
   double a = kAtanT[2 * i] + (fma(r * r2, p, r) + kAtanT[2 * i + 1]);
-  a = (ay > ax) ? (kNum[3] - a) + kNum[4] : a;
+  a = steep ? (kNum[3] - a) + kNum[4] : a;
   a = (x < 0.0) ? (kNum[5] - a) + kNum[6] : a;
   a = (mx == 0.0) ? 0.0 : a;
   return (y < 0.0) ? -a : a;
+}
+
+__device__ SS_COLD double2 sincos_cold(double b) {
+  double s, c;
+  sincos(b, &s, &c);
+  return make_double2(s, c);
 }
 
 // sin and cos of a small angle (|b| <= 0.26 rad ~ 15 deg: the transverse stream
@@ -244,7 +268,9 @@ __device__ __forceinline__ void sincos_small(double b, double& s, double& c) {
     s = b * ps;
     c = fma(pc, x, 1.0);
   } else {
-    sincos(b, &s, &c);
+    const double2 sc = sincos_cold(b);
+    s = sc.x;
+    c = sc.y;
   }
 }
 

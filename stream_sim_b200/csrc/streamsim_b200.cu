@@ -58,6 +58,10 @@ struct KArgs {
   unsigned long long n, offset, seed;
   int blob_in_smem;
   uint32_t blob_bytes;
+  // derived launch constants (filled by ss_run): the Philox round keys of `seed` and the
+  // histogram origins / inverse bin widths rounded to fp32
+  ss::PhiloxKeys keys;
+  float hist_lo[SS_N_HIST], hist_inv[SS_N_HIST];
 };
 
 // ---------------------------------------------------------------- smem staging
@@ -442,7 +446,7 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
       const bool z_dist = p.dist_sampler == SS_SAMPLER_GAUSSIAN;
       const bool all_given = d_u_phi1 && (d_u_mass || !has_iso) && d_n_phi2 && (d_n_dist || !has_dist);
       uint4 w = make_uint4(0u, 0u, 0u, 0u);
-      if (!all_given) w = ss::philox_block(gi, SS_DRAW_BLOCK_POS, a.seed);
+      if (!all_given) w = ss::philox_block(gi, SS_DRAW_BLOCK_POS, a.keys);
       double u_phi1 = d_u_phi1 ? d_u_phi1[i] : ss::u32(w.x);
       const double u_mass = d_u_mass ? d_u_mass[i] : ss::u32(w.y);
       double z0 = 0, z1 = 0;
@@ -463,7 +467,7 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
       } else if (density_kind == SS_DENSITY_GAUSSIAN) {  // the u_phi1 slot carries a normal draw
         if (!d_u_phi1) {
           double zz;
-          const uint4 wz4 = ss::philox_block(gi, SS_DRAW_BLOCK_DENSITY_Z, a.seed);
+          const uint4 wz4 = ss::philox_block(gi, SS_DRAW_BLOCK_DENSITY_Z, a.keys);
           ss::bm32(wz4.x, wz4.y, u_phi1, zz);
         }
         phi1 = __dadd_rn(__dmul_rn(u_phi1, p.density_hi), p.density_lo);
@@ -566,7 +570,7 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
       uint4 w = make_uint4(0u, 0u, 0u, 0u);
       double z_r = 0, z_g = 0;
       if (!all_given) {
-        w = ss::philox_block(gi, SS_DRAW_BLOCK_OBS, a.seed);
+        w = ss::philox_block(gi, SS_DRAW_BLOCK_OBS, a.keys);
         ss::bm32(w.x, w.y, z_r, z_g);
       }
       if (d_z_g) z_g = d_z_g[i];
@@ -609,7 +613,7 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
 #pragma unroll
       for (int h = 0; h < SS_N_HIST; ++h) {
         if (!hb[h]) continue;
-        const int bin = ss::hist_bin((float)hv[h], (float)p.hist_lo[h], (float)p.hist_inv_width[h]);
+        const int bin = ss::hist_bin((float)hv[h], a.hist_lo[h], a.hist_inv[h]);
         if (bin >= 0) atomicAdd(&s_hist[h * SS_HIST_BINS + bin], 1u);
       }
     }
@@ -646,14 +650,20 @@ k_fused(const __grid_constant__ KArgs a) {
   extern __shared__ __align__(16) unsigned char smem_blob[];
   __shared__ unsigned long long s_bar;
   __shared__ unsigned int s_cnt[SS_N_COUNTERS];
-  __shared__ unsigned int s_hist[HIST ? SS_N_HIST * SS_HIST_BINS : 1];
+  // one extra slot at the end collects the out-of-range values: no branch around the atomics
+  __shared__ unsigned int s_hist[HIST ? SS_N_HIST * SS_HIST_BINS + 1 : 1];
+  constexpr int kDump = SS_N_HIST * SS_HIST_BINS;
 
   const SSParams& p = a.p;
   const bool want_cnt = a.o.counters != nullptr;
   const int share = ss::curve_share(p);
   for (int i = threadIdx.x; i < SS_N_COUNTERS; i += blockDim.x) s_cnt[i] = 0;
   if (HIST)
-    for (int i = threadIdx.x; i < SS_N_HIST * SS_HIST_BINS; i += blockDim.x) s_hist[i] = 0;
+    for (int i = threadIdx.x; i <= kDump; i += blockDim.x) s_hist[i] = 0;
+  // The five per-star summary counts live in three registers as 16-bit fields (a thread
+  // sees at most 2^31 / (148 * 1024) < 2^16 stars per launch) and are reduced once, after
+  // the loop: one add per count and star instead of a warp reduction and a shared atomic.
+  uint32_t c_unseen_badg = 0, c_badr_obs = 0, c_perfect = 0;
   stage_blob(smem_blob, a.t.blob, a.blob_bytes, &s_bar);
   const double* const tab = reinterpret_cast<const double*>(smem_blob);
   __syncthreads();
@@ -669,7 +679,7 @@ k_fused(const __grid_constant__ KArgs a) {
   uint4 wp = make_uint4(0u, 0u, 0u, 0u);
   double2 eg = make_double2(0.0, 0.0), ei = make_double2(0.0, 0.0);
   auto prepare = [&](uint32_t star) {
-    wp = ss::philox_block(a.offset + star, SS_DRAW_BLOCK_POS, a.seed);
+    wp = ss::philox_block(a.offset + star, SS_DRAW_BLOCK_POS, a.keys);
     // bucket = floor(u * buckets), u = w / 2^32, buckets a power of two: the high word of w * buckets
     eg = __ldg(&grid_lut[__umulhi(wp.x, grid_lut_n)]);
     ei = __ldg(&iso_lut[__umulhi(wp.y, iso_lut_n)]);
@@ -716,12 +726,12 @@ k_fused(const __grid_constant__ KArgs a) {
     put<OutT>(a.o.mag[SS_BAND_R], i, mag_r);
     if (HIST) {
       const int b0 = __double2loint(row.thr);                        // host-binned phi1
-      if (b0 >= 0) atomicAdd(&s_hist[b0], 1u);
+      atomicAdd(&s_hist[b0 >= 0 ? b0 : kDump], 1u);
       const float hv[4] = {(float)phi2, (float)dist, (float)mag_g, (float)(mag_g - mag_r)};
 #pragma unroll
       for (int h = 1; h < SS_N_HIST; ++h) {
-        const int bin = ss::hist_bin(hv[h - 1], (float)p.hist_lo[h], (float)p.hist_inv_width[h]);
-        if (bin >= 0) atomicAdd(&s_hist[h * SS_HIST_BINS + bin], 1u);
+        const int bin = ss::hist_bin(hv[h - 1], a.hist_lo[h], a.hist_inv[h]);
+        atomicAdd(&s_hist[bin >= 0 ? h * SS_HIST_BINS + bin : kDump], 1u);
       }
     }
 
@@ -757,7 +767,7 @@ k_fused(const __grid_constant__ KArgs a) {
       if (want_cnt) atomicAdd(&s_cnt[SS_CNT_BADCOORD], 1u);
       if (a.o.pix) a.o.pix[i] = -1;
     }
-    const uint4 wo = ss::philox_block(a.offset + i, SS_DRAW_BLOCK_OBS, a.seed);
+    const uint4 wo = ss::philox_block(a.offset + i, SS_DRAW_BLOCK_OBS, a.keys);
     double z_r, z_g;
     ss::bm32(wo.x, wo.y, z_r, z_g);
     ss::ObsOut o;
@@ -769,17 +779,20 @@ k_fused(const __grid_constant__ KArgs a) {
     put<OutT>(a.o.magerr[SS_BAND_R], i, o.err[SS_BAND_R]);
     if (a.o.flag_observed) a.o.flag_observed[i] = o.observed ? 1 : 0;
     if (a.o.flag_perfect) a.o.flag_perfect[i] = o.perfect ? 1 : 0;
-    SS_COUNT(SS_CNT_UNSEEN, o.unseen);
-    SS_COUNT(SS_CNT_BADMAG_G, o.bad[SS_BAND_G]);
-    SS_COUNT(SS_CNT_BADMAG_R, o.bad[SS_BAND_R]);
-    SS_COUNT(SS_CNT_OBSERVED, o.observed);
-    if (p.perfect_galstarsep) SS_COUNT(SS_CNT_PERFECT, o.perfect);
+    c_unseen_badg += (o.unseen ? 1u : 0u) + (o.bad[SS_BAND_G] ? 0x10000u : 0u);
+    c_badr_obs += (o.bad[SS_BAND_R] ? 1u : 0u) + (o.observed ? 0x10000u : 0u);
+    c_perfect += o.perfect ? 1u : 0u;
 
     if (i + stride < n) prepare(i + stride);                       // n <= 2^31: no wrap-around
   }
 
   if (want_cnt) {
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&a.o.counters[SS_CNT_TOTAL], a.n);
+    atomicAdd(&s_cnt[SS_CNT_UNSEEN], c_unseen_badg & 0xffffu);
+    atomicAdd(&s_cnt[SS_CNT_BADMAG_G], c_unseen_badg >> 16);
+    atomicAdd(&s_cnt[SS_CNT_BADMAG_R], c_badr_obs & 0xffffu);
+    atomicAdd(&s_cnt[SS_CNT_OBSERVED], c_badr_obs >> 16);
+    atomicAdd(&s_cnt[SS_CNT_PERFECT], c_perfect);
     __syncthreads();
     for (int k = threadIdx.x; k < SS_N_COUNTERS; k += blockDim.x)
       if (s_cnt[k]) atomicAdd(&a.o.counters[k], (unsigned long long)s_cnt[k]);
@@ -871,7 +884,7 @@ __global__ void k_math_probe(int fn, const double* x, const double* y2, double* 
 // draw is injected or the star's z_phi2 / u_phi2 (POS block words 2, 3)
 __global__ void k_loc_scale(int normal, const double* loc, const double* scale, double loc0,
                             double scale0, const double* draws, double* out, unsigned long long n,
-                            unsigned long long offset, unsigned long long seed) {
+                            unsigned long long offset, const ss::PhiloxKeys keys) {
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += stride) {
@@ -879,7 +892,7 @@ __global__ void k_loc_scale(int normal, const double* loc, const double* scale, 
     if (draws) {
       d = draws[i];
     } else {
-      const uint4 w = ss::philox_block(offset + i, SS_DRAW_BLOCK_POS, seed);
+      const uint4 w = ss::philox_block(offset + i, SS_DRAW_BLOCK_POS, keys);
       double z0, z1;
       ss::bm32(w.z, w.w, z0, z1);
       d = normal ? z0 : ss::u32(w.z);
@@ -893,7 +906,7 @@ __global__ void k_loc_scale(int normal, const double* loc, const double* scale, 
 // z injected or the star's z_r (OBS block words 0, 1)
 __global__ void k_noisy_mag(const double* mag, const double* err, const double* z_in, double* out,
                             unsigned long long n, unsigned long long offset,
-                            unsigned long long seed) {
+                            const ss::PhiloxKeys keys) {
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += stride) {
@@ -901,7 +914,7 @@ __global__ void k_noisy_mag(const double* mag, const double* err, const double* 
     if (z_in) {
       z = z_in[i];
     } else {
-      const uint4 w = ss::philox_block(offset + i, SS_DRAW_BLOCK_OBS, seed);
+      const uint4 w = ss::philox_block(offset + i, SS_DRAW_BLOCK_OBS, keys);
       double z1;
       ss::bm32(w.x, w.y, z, z1);
     }
@@ -916,17 +929,30 @@ __global__ void k_noisy_mag(const double* mag, const double* err, const double* 
 // (OBS block word 2)
 __global__ void k_bernoulli(const double* prob, const double* u_in, uint8_t* out,
                             unsigned long long n, unsigned long long offset,
-                            unsigned long long seed) {
+                            const ss::PhiloxKeys keys) {
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += stride) {
     const double u = u_in ? u_in[i]
-                          : ss::u32(ss::philox_block(offset + i, SS_DRAW_BLOCK_OBS, seed).z);
+                          : ss::u32(ss::philox_block(offset + i, SS_DRAW_BLOCK_OBS, keys).z);
     out[i] = (u <= prob[i]) ? 1 : 0;
   }
 }
 
 // ---------------------------------------------------------------- host side
+// Philox4x32 key schedule of a 64-bit seed: round r uses key + r * (0x9E3779B9, 0xBB67AE85)
+ss::PhiloxKeys philox_keys(unsigned long long seed) {
+  ss::PhiloxKeys K;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  for (int r = 0; r < 10; ++r) {
+    K.rk[2 * r] = k0;
+    K.rk[2 * r + 1] = k1;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return K;
+}
+
 struct DevInfo {
   int device = -1, sms = 0, smem_optin = 0;
 };
@@ -1206,6 +1232,11 @@ int ss_run(uint32_t stages, const SSParams* p, const SSTables* t, const SSMaps* 
   a.n = n;
   a.offset = star_offset;
   a.seed = seed;
+  a.keys = philox_keys(seed);
+  for (int h = 0; h < SS_N_HIST; ++h) {
+    a.hist_lo[h] = (float)p->hist_lo[h];
+    a.hist_inv[h] = (float)p->hist_inv_width[h];
+  }
   int smem, grid;
   if (a.t.blob_hot_bytes <= 0 || a.t.blob_hot_bytes > a.t.blob_bytes)
     a.t.blob_hot_bytes = a.t.blob_bytes;
@@ -1349,7 +1380,7 @@ int ss_loc_scale(int32_t normal, const double* loc, const double* scale, double 
   int grid, rc;
   if ((rc = small_grid(n, &grid))) return rc;
   k_loc_scale<<<grid, 256, 0, (cudaStream_t)stream>>>(normal, loc, scale, loc0, scale0, draws, out,
-                                                      n, star_offset, seed);
+                                                      n, star_offset, philox_keys(seed));
   SS_CUDA(cudaGetLastError());
   return SS_OK;
 }
@@ -1360,7 +1391,8 @@ int ss_noisy_magnitudes(const double* mag, const double* err, const double* z, d
   if (n == 0) return SS_OK;
   int grid, rc;
   if ((rc = small_grid(n, &grid))) return rc;
-  k_noisy_mag<<<grid, 256, 0, (cudaStream_t)stream>>>(mag, err, z, out, n, star_offset, seed);
+  k_noisy_mag<<<grid, 256, 0, (cudaStream_t)stream>>>(mag, err, z, out, n, star_offset,
+                                                      philox_keys(seed));
   SS_CUDA(cudaGetLastError());
   return SS_OK;
 }
@@ -1371,7 +1403,8 @@ int ss_bernoulli(const double* prob, const double* u, uint8_t* out, uint64_t n,
   if (n == 0) return SS_OK;
   int grid, rc;
   if ((rc = small_grid(n, &grid))) return rc;
-  k_bernoulli<<<grid, 256, 0, (cudaStream_t)stream>>>(prob, u, out, n, star_offset, seed);
+  k_bernoulli<<<grid, 256, 0, (cudaStream_t)stream>>>(prob, u, out, n, star_offset,
+                                                      philox_keys(seed));
   SS_CUDA(cudaGetLastError());
   return SS_OK;
 }

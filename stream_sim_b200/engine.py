@@ -437,6 +437,7 @@ class StarEngine:
         self.tables.iso_thr = self.iso_thr.data_ptr()
         p.iso_direct, p.iso_n, p.iso_lut_n = 1, n, ISO_LUT
 
+
     def _pack_iso_tables(self, tab, packer):
         """Two-stage tables in the shared-memory blob (csrc ``iso_sample``)."""
         p = self.params
