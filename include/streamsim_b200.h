@@ -147,6 +147,17 @@ typedef struct SSFunc {
   int32_t g_n;
   int32_t g_off, pad_;
   double g_x0, g_inv;
+  /* optional direct look-up form of a LINEAR table (the survey curves in the production
+   * kernel): no search, no range / NaN selects.
+   *   segments  seg[q_nseg][4 doubles] = (x_j, f_j, slope_j, 0) at q_seg_off: the table's own
+   *     intervals framed by constant ones for x below the first knot (fill), at the last
+   *     knot and above it (fill), so that  value = slope * (x - x_j) + f_j  (two roundings)
+   *     is interp1d's answer for every finite or NaN x;
+   *   buckets   rec[q_n + 2][4 doubles] = (x_a, x_b, j as int32 in the low word, 0) at q_off:
+   *     bucket = clamp(floor((x - q_x0) * q_inv) + 1, 0, q_n + 1), interval = j + (x >= x_a)
+   *     + (x >= x_b)  (+inf = no such knot).  q_n = 0: absent. */
+  int32_t q_n, q_off, q_seg_off, q_nseg;
+  double q_x0, q_inv;
 } SSFunc;
 
 typedef struct SSParams {
@@ -236,9 +247,11 @@ typedef struct SSTables {
   const double* grid_rows;
   const double* grid_lut;
   const double* grid_thr;
-  /* iso_direct: rows[iso_n][6] = (U_k, mag_g, dmag_g/du, mag_r, dmag_r/du, 0) on the union of
-   * the IMF-CDF knots and the isochrone knots mapped to u; thr[k] = U_{k+1} (last = +inf);
-   * lut[iso_lut_n][2] packed exactly like grid_lut. */
+  /* iso_direct: rows[iso_n][4] = (a_g, dmag_g/du, a_r, dmag_r/du) on the union of the
+   * IMF-CDF knots and the isochrone knots mapped to u: mag_b(u) = fma(slope_b, u, a_b) inside
+   * segment k (a_b = mag_b(U_k) - slope_b * U_k, folded on the host in extended precision);
+   * 32-byte aligned.  thr[k] = U_{k+1} (last = +inf); lut[iso_lut_n][2] packed exactly like
+   * grid_lut.  grid_rows and SSMaps.packed must be 32-byte aligned as well. */
   const double* iso_rows;
   const double* iso_lut;
   const double* iso_thr;

@@ -35,7 +35,9 @@ class SSFunc(C.Structure):
     _fields_ = [("kind", _i32), ("n", _i32), ("x_off", _i32), ("c_off", _i32),
                 ("xmin", _f64), ("xmax", _f64), ("p", _f64 * 4),
                 ("n2", _i32), ("x2_off", _i32), ("c2_off", _i32), ("g_n", _i32),
-                ("g_off", _i32), ("pad_", _i32), ("g_x0", _f64), ("g_inv", _f64)]
+                ("g_off", _i32), ("pad_", _i32), ("g_x0", _f64), ("g_inv", _f64),
+                ("q_n", _i32), ("q_off", _i32), ("q_seg_off", _i32), ("q_nseg", _i32),
+                ("q_x0", _f64), ("q_inv", _f64)]
 
 
 class SSParams(C.Structure):

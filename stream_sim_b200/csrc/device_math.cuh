@@ -609,6 +609,43 @@ __device__ __forceinline__ double efficiency_at(const SSParams& p, const SSFunc&
   return (maglim < sat || maglim != maglim) ? 0.0 : r;
 }
 
+// the same two getters on the direct look-up form of the curves (SSFunc.q_*): the framed
+// segment records answer every range / NaN case by themselves
+__device__ __forceinline__ int q_locate(const SSFunc& f, const double* __restrict__ tab, double x) {
+  int b = __double2int_rd(__dmul_rn(__dsub_rn(x, f.q_x0), f.q_inv)) + 1;     // NaN -> 1
+  b = max(0, min(b, f.q_n + 1));
+  const double2* __restrict__ rec = reinterpret_cast<const double2*>(tab + f.q_off) + 2 * b;
+  const double2 r0 = rec[0];
+  const int j = __double2loint(rec[1].x);
+  return j + (x >= r0.x ? 1 : 0) + (x >= r0.y ? 1 : 0);
+}
+
+__device__ __forceinline__ double q_value(const SSFunc& f, const double* __restrict__ tab, int j,
+                                          double x) {
+  const double2* __restrict__ seg = reinterpret_cast<const double2*>(tab + f.q_seg_off) + 2 * j;
+  const double2 s0 = seg[0];
+  const double slope = seg[1].x;
+  return __dadd_rn(__dmul_rn(slope, __dsub_rn(x, s0.x)), s0.y);
+}
+
+__device__ __forceinline__ double photo_error_log_q(const SSParams& p, const double* __restrict__ tab,
+                                                    double sat, double mag, double delta, int j,
+                                                    bool& bright) {
+  bright = mag < sat;
+  const double v = q_value(p.photo_error, tab, j, delta);
+  const double w = (delta <= p.delta_saturation && mag >= sat) ? p.log_err_at_dsat : v;
+  return bright ? 0.0 : w;
+}
+
+__device__ __forceinline__ double efficiency_q(const SSParams& p, const SSFunc& f,
+                                               const double* __restrict__ tab, double sat,
+                                               double mag, double maglim, double delta, int j) {
+  double r = q_value(f, tab, j, delta);
+  r = (mag > sat && delta <= p.delta_saturation) ? 1.0 : r;
+  r = (mag < sat) ? 0.0 : r;
+  return (maglim < sat || maglim != maglim) ? 0.0 : r;
+}
+
 // ---------------------------------------------------------------- per-star observe arithmetic
 // Everything of StreamInjector.inject's per-star body that follows the map gathers
 // (reference observed.py:163-291), shared by the generic kernel and the production
@@ -666,12 +703,16 @@ __device__ __forceinline__ int curve_share(const SSParams& p) {
   const SSFunc& e = p.photo_error;
   const SSFunc& c = p.completeness;
   const SSFunc& d = p.detection;
-  const int sc = (c.n == e.n && c.x_off == e.x_off && c.g_n == e.g_n && c.g_off == e.g_off) ? 1 : 0;
-  const int sd = (d.n == e.n && d.x_off == e.x_off && d.g_n == e.g_n && d.g_off == e.g_off) ? 2 : 0;
+  const int sc = (c.n == e.n && c.x_off == e.x_off && c.g_n == e.g_n && c.g_off == e.g_off &&
+                  c.q_n == e.q_n && c.q_off == e.q_off) ? 1 : 0;
+  const int sd = (d.n == e.n && d.x_off == e.x_off && d.g_n == e.g_n && d.g_off == e.g_off &&
+                  d.q_n == e.q_n && d.q_off == e.q_off) ? 2 : 0;
   return sc | sd;
 }
 
-template <int MATH>
+// QCURVE: the survey curves are read through their direct look-up form (the production
+// kernel; the launcher checks that every curve has one), else through the guided search.
+template <int MATH, bool QCURVE = false>
 __device__ __forceinline__ void observe_star(const SSParams& p, const double* __restrict__ tab,
                                              int share, bool band_g, bool band_r, double mag_g,
                                              double mag_r, double ebv, double ml_g, double ml_r,
@@ -698,8 +739,13 @@ __device__ __forceinline__ void observe_star(const SSParams& p, const double* __
     j2[b] = 0;
     o.err[b] = o.mobs[b] = nan_d();
     if (!have2[b]) continue;
-    j2[b] = lin_locate(p.photo_error, tab, dl2[b]);
-    loge2[b] = photo_error_log_at(p, tab, p.saturation[b], mt2[b], dl2[b], j2[b], bright2[b]);  // surveys.py:234-286
+    if (QCURVE) {
+      j2[b] = q_locate(p.photo_error, tab, dl2[b]);
+      loge2[b] = photo_error_log_q(p, tab, p.saturation[b], mt2[b], dl2[b], j2[b], bright2[b]);
+    } else {
+      j2[b] = lin_locate(p.photo_error, tab, dl2[b]);
+      loge2[b] = photo_error_log_at(p, tab, p.saturation[b], mt2[b], dl2[b], j2[b], bright2[b]);  // surveys.py:234-286
+    }
     plain = plain && fabs(mt2[b]) < 200.0 && !(fabs(loge2[b]) >= 300.0);
   }
   // completeness / detection Bernoulli trials in the survey's completeness band (observed.py:224-243)
@@ -707,12 +753,21 @@ __device__ __forceinline__ void observe_star(const SSParams& p, const double* __
   const double mt_c = cr ? mt2[1] : mt2[0], ml_c = cr ? ml2[1] : ml2[0], dl_c = cr ? dl2[1] : dl2[0];
   const double sat_c = cr ? p.saturation[1] : p.saturation[0];
   const int j_p = cr ? j2[1] : j2[0];
-  const int j_c = (share & 1) ? j_p : lin_locate(p.completeness, tab, dl_c);
-  const bool flag_c = u_det <= efficiency_at(p, p.completeness, tab, sat_c, mt_c, ml_c, dl_c, j_c);
-  bool flag_d = false;
-  if (p.perfect_galstarsep) {
-    const int j_d = (share & 2) ? j_p : lin_locate(p.detection, tab, dl_c);
-    flag_d = u_det2 <= efficiency_at(p, p.detection, tab, sat_c, mt_c, ml_c, dl_c, j_d);
+  bool flag_c, flag_d = false;
+  if (QCURVE) {
+    const int j_c = (share & 1) ? j_p : q_locate(p.completeness, tab, dl_c);
+    flag_c = u_det <= efficiency_q(p, p.completeness, tab, sat_c, mt_c, ml_c, dl_c, j_c);
+    if (p.perfect_galstarsep) {
+      const int j_d = (share & 2) ? j_p : q_locate(p.detection, tab, dl_c);
+      flag_d = u_det2 <= efficiency_q(p, p.detection, tab, sat_c, mt_c, ml_c, dl_c, j_d);
+    }
+  } else {
+    const int j_c = (share & 1) ? j_p : lin_locate(p.completeness, tab, dl_c);
+    flag_c = u_det <= efficiency_at(p, p.completeness, tab, sat_c, mt_c, ml_c, dl_c, j_c);
+    if (p.perfect_galstarsep) {
+      const int j_d = (share & 2) ? j_p : lin_locate(p.detection, tab, dl_c);
+      flag_d = u_det2 <= efficiency_at(p, p.detection, tab, sat_c, mt_c, ml_c, dl_c, j_d);
+    }
   }
   o.unseen = ml_c != ml_c;
   if (plain) {

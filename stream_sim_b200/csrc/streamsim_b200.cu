@@ -32,6 +32,10 @@
 #ifndef SS_FUSED_MIN_CTAS
 #define SS_FUSED_MIN_CTAS 1
 #endif
+// 1: k_fused reads the survey curves through their direct look-up form (SSFunc.q_*)
+#ifndef SS_QCURVE
+#define SS_QCURVE 1
+#endif
 
 namespace {
 
@@ -174,12 +178,27 @@ __device__ __forceinline__ int step_scan(const double* __restrict__ thr, int lo,
   return j;
 }
 
+// 32 bytes per lane in ONE load instruction (LDG.E.ENL2.256, read-only path): the scattered
+// table records cost the L1 data pipe one pass per instruction and lane, whatever the width --
+// the kernel's busiest unit -- so a 64-byte row is fetched as two of these instead of four
+// 16-byte loads.  `p` must be 32-byte aligned.
+struct __align__(32) Double4 {
+  double a, b, c, d;
+};
+
+__device__ __forceinline__ Double4 ldg256(const void* p) {
+  Double4 r;
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+      : "=d"(r.a), "=d"(r.b), "=d"(r.c), "=d"(r.d)
+      : "l"(p));
+  return r;
+}
+
 __device__ __forceinline__ void load_grid_row(const double* __restrict__ grid_rows, long long idx,
                                               GridRow& row) {
-  const double2* __restrict__ rows = reinterpret_cast<const double2*>(grid_rows) + 4 * idx;
-  const double2 r0 = __ldg(rows), r1 = __ldg(rows + 1), r2 = __ldg(rows + 2), r3 = __ldg(rows + 3);
-  row.thr = r0.x; row.x = r0.y; row.c = r1.x; row.s = r1.y;
-  row.dc = r2.x; row.ds = r2.y; row.sinx = r3.x; row.cosx = r3.y;
+  const Double4 r0 = ldg256(grid_rows + 8 * idx), r1 = ldg256(grid_rows + 8 * idx + 4);
+  row.thr = r0.a; row.x = r0.b; row.c = r0.c; row.s = r0.d;
+  row.dc = r1.a; row.ds = r1.b; row.sinx = r1.c; row.cosx = r1.d;
 }
 
 // inverse_transform_sample (reference samplers.py:55-76) as a direct lookup: the
@@ -255,14 +274,14 @@ __device__ __forceinline__ double invcdf_phi1(const KArgs& a, const int32_t* __r
 // tabulates that composite (values at the breakpoints from the reference's own two-stage
 // arithmetic) and the device finds the segment with the same one-round-trip bucket table
 // as the phi1 grid: no search loops in shared memory, no division, 100 KB less shared
-// memory.  Rows: (U_k, g_k, dg/du, r_k, dr/du, 0); thr[k] = U_{k+1}.
+// memory.  Rows: 32 bytes = (a_g, dg/du, a_r, dr/du) with mag_b(u) = fma(slope_b, u, a_b) inside
+// segment k, a_b = mag_b(U_k) - slope_b * U_k folded on the host in extended precision: one
+// 256-bit load per star.  thr[k] = U_{k+1}.
 __device__ __forceinline__ void iso_row_eval(const double* __restrict__ iso_rows, long long idx,
                                              double u, double& m1, double& m2) {
-  const double2* __restrict__ rows = reinterpret_cast<const double2*>(iso_rows) + 3 * idx;
-  const double2 r0 = __ldg(rows), r1 = __ldg(rows + 1), r2 = __ldg(rows + 2);
-  const double du = u - r0.x;
-  m1 = r0.y + r1.x * du;
-  m2 = r1.y + r2.x * du;
+  const Double4 r = ldg256(iso_rows + 4 * idx);
+  m1 = fma(r.b, u, r.a);
+  m2 = fma(r.d, u, r.c);
 }
 
 __device__ __forceinline__ void iso_sample_direct(const KArgs& a, double u, double& m1, double& m2,
@@ -749,9 +768,8 @@ k_fused(const __grid_constant__ KArgs a) {
     if (L.valid) {
       const long long pe = ss::hp_ring(L, p.nside_ebv);
       if (PACKED) {
-        const double2* __restrict__ rec = reinterpret_cast<const double2*>(a.m.packed) + 2 * pe;
-        const double2 r0 = __ldg(rec), r1 = __ldg(rec + 1);
-        ebv = r0.x; ml_g = r0.y; ml_r = r1.x;
+        const Double4 r = ldg256(a.m.packed + 4 * pe);
+        ebv = r.a; ml_g = r.b; ml_r = r.c;
       } else {
         ebv = __ldg(&a.m.ebv[pe]);
         const long long pg = (p.nside_maglim[SS_BAND_G] == p.nside_ebv)
@@ -771,8 +789,8 @@ k_fused(const __grid_constant__ KArgs a) {
     double z_r, z_g;
     ss::bm32(wo.x, wo.y, z_r, z_g);
     ss::ObsOut o;
-    ss::observe_star<MATH>(p, tab, share, true, true, mag_g, mag_r, ebv, ml_g, ml_r, z_g, z_r,
-                           ss::u32(wo.z), ss::u32(wo.w), o);
+    ss::observe_star<MATH, SS_QCURVE != 0>(p, tab, share, true, true, mag_g, mag_r, ebv, ml_g, ml_r, z_g,
+                                 z_r, ss::u32(wo.z), ss::u32(wo.w), o);
     put<OutT>(a.o.mag_obs[SS_BAND_G], i, o.mobs[SS_BAND_G]);
     put<OutT>(a.o.magerr[SS_BAND_G], i, o.err[SS_BAND_G]);
     put<OutT>(a.o.mag_obs[SS_BAND_R], i, o.mobs[SS_BAND_R]);
@@ -1013,7 +1031,8 @@ bool fused_eligible(const KArgs& a, int smem) {
          p.has_iso && p.iso_direct && p.band_present[0] && p.band_present[1] &&
          !d.u_phi1 && !d.u_mass && !d.n_phi2 && !d.n_dist && !d.z_flux[0] && !d.z_flux[1] &&
          !d.u_det && !d.u_det2 && !a.in.phi1 && !a.in.phi2 && !a.in.dist && !a.o.draws_out &&
-         a.n <= (1ULL << 31);
+         p.photo_error.q_n > 0 && p.completeness.q_n > 0 &&
+         (!p.perfect_galstarsep || p.detection.q_n > 0) && a.n <= (1ULL << 31);
 }
 
 template <typename OutT, int MATH, bool HIST>
@@ -1067,6 +1086,10 @@ int check_func(const SSFunc& f, int64_t blob_doubles, const char* name) {
     if (f.n < 2 || f.x_off < 0 || f.c_off < 0 || f.x_off + (int64_t)f.n > blob_doubles ||
         f.c_off + need_c > blob_doubles)
       return fail(SS_EINVAL, "function table '%s' lies outside the blob", name);
+    if (f.q_n != 0 &&
+        (f.q_n < 1 || f.q_nseg < 3 || f.q_off < 0 || f.q_seg_off < 0 || (f.q_off & 1) || (f.q_seg_off & 1) ||
+         f.q_off + 4LL * (f.q_n + 2) > blob_doubles || f.q_seg_off + 4LL * f.q_nseg > blob_doubles))
+      return fail(SS_EINVAL, "direct look-up table of '%s' lies outside the blob", name);
   } else if (f.kind < SS_FN_NONE || f.kind > SS_FN_SPLINE_PRODUCT) {
     return fail(SS_EINVAL, "unknown function kind in '%s'", name);
   }
@@ -1098,6 +1121,7 @@ int validate(uint32_t st, const SSParams* p, const SSTables* t, const SSMaps* m,
     if (p->density_kind == SS_DENSITY_GRID) {
       if (!t->grid_rows || !t->grid_lut || !t->grid_thr || p->grid_nthr < 0 || p->grid_lut_n < 1)
         return fail(SS_EINVAL, "grid density needs grid_rows, grid_lut and grid_thr%s");
+      if ((uintptr_t)t->grid_rows & 31) return fail(SS_EINVAL, "grid_rows must be 32-byte aligned%s");
       // u * buckets must be exact for bucket = floor(u * buckets) to agree with the host's edges
       if (p->grid_lut_n & (p->grid_lut_n - 1)) return fail(SS_EINVAL, "grid_lut_n must be a power of two%s");
     }
@@ -1112,6 +1136,7 @@ int validate(uint32_t st, const SSParams* p, const SSTables* t, const SSMaps* m,
       if (p->iso_direct) {
         if (!t->iso_rows || !t->iso_lut || !t->iso_thr || p->iso_n < 2 || p->iso_lut_n < 1)
           return fail(SS_EINVAL, "direct isochrone lookup needs iso_rows, iso_lut, iso_thr%s");
+        if ((uintptr_t)t->iso_rows & 31) return fail(SS_EINVAL, "iso_rows must be 32-byte aligned%s");
         if (p->iso_lut_n & (p->iso_lut_n - 1)) return fail(SS_EINVAL, "iso_lut_n must be a power of two%s");
       } else {
         if (p->iso_n < 2 || p->imf_n < 2) return fail(SS_EINVAL, "isochrone/IMF tables too short%s");
@@ -1128,6 +1153,8 @@ int validate(uint32_t st, const SSParams* p, const SSTables* t, const SSMaps* m,
     if (!p->band_present[SS_BAND_R])
       return fail(SS_EINVAL, "band 'r' is required (reference observed.py:256)%s");
     if (!m->ebv) return fail(SS_EINVAL, "E(B-V) map not loaded%s");
+    if (m->packed && ((uintptr_t)m->packed & 31))
+      return fail(SS_EINVAL, "SSMaps.packed must be 32-byte aligned%s");
     for (int b = 0; b < 2; ++b)
       if (p->band_present[b] && !m->maglim[b]) return fail(SS_EINVAL, "maglim map missing for a requested band%s");
     if (!p->band_present[p->completeness_band & 1])

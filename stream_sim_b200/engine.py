@@ -69,11 +69,16 @@ class BlobPacker:
         self._nd = 0
         self._seen = {}
 
-    def add_doubles(self, arr, dedupe=False):
+    def add_doubles(self, arr, dedupe=False, align=1):
+        """``align``: offset a multiple of this many doubles (2 for records read as double2)."""
         arr = np.ascontiguousarray(arr, dtype=np.float64).ravel()
-        key = arr.tobytes() if dedupe else None
+        key = (arr.tobytes(), align) if dedupe else None
         if key is not None and key in self._seen:
             return self._seen[key]
+        if self._nd % align:
+            pad = align - self._nd % align
+            self._d.append(np.zeros(pad))
+            self._nd += pad
         off = self._nd
         self._d.append(arr)
         self._nd += arr.size
@@ -128,6 +133,51 @@ class BlobPacker:
                       p=(0.0, 0.0, float(xs[0]), float(xs[-1])))   # p[2:4] = table range (lin_eval)
         fields.update(self.add_bucket_guide(xs))
         return fields
+
+    def add_direct_lookup(self, x, y, fill):
+        """Direct look-up form of an ``interp1d(kind='linear', bounds_error=False,
+        fill_value=fill)`` table (``SSFunc.q_*``, include/streamsim_b200.h): framed segment
+        records + a uniform bucket table whose entries settle the interval with at most two
+        compares.  Returns the q_* fields, or {} when the table does not lend itself to it
+        (duplicate abscissae, or knots too crowded for 4096 buckets)."""
+        x = np.asarray(x, dtype=float)
+        y = np.asarray(y, dtype=float)
+        order = np.argsort(x, kind="mergesort")
+        xs, ys = x[order], y[order]
+        n = len(xs)
+        span = xs[-1] - xs[0]
+        if n < 2 or not np.all(np.isfinite(xs)) or np.any(np.diff(xs) <= 0) or not np.isfinite(span):
+            return {}
+        slope = (ys[1:] - ys[:-1]) / (xs[1:] - xs[:-1])
+        if not np.all(np.isfinite(slope) | np.isnan(ys[1:] - ys[:-1])):
+            return {}
+        fill = float(fill)
+        top = np.nextafter(xs[-1], np.inf)
+        # lower ends of the framed intervals, and their records
+        knots = np.concatenate([[-np.inf], xs, [top]])
+        seg = np.zeros((n + 2, 4))
+        seg[0] = (0.0, fill, 0.0, 0.0)
+        seg[1:n, 0], seg[1:n, 1], seg[1:n, 2] = xs[:-1], ys[:-1], slope
+        seg[n] = (xs[-1], ys[-1], 0.0, 0.0)
+        seg[n + 1] = (0.0, fill, 0.0, 0.0)
+        for nb in (256, 512, 1024, 2048, 4096):
+            inv = nb / span
+            d = (abs(xs[0]) + span) * 1e-12            # rounding of (x - x0) * inv at a bucket edge
+            lo_edge = np.concatenate([[-np.inf], xs[0] + np.arange(nb + 1) / inv - d])
+            hi_edge = np.concatenate([xs[0] + np.arange(nb + 1) / inv + d, [np.inf]])
+            base = np.searchsorted(knots, lo_edge, side="right") - 1       # last knot <= every x of the bucket
+            inside = np.searchsorted(knots, hi_edge, side="right") - 1 - base
+            if inside.max() <= 2:
+                break
+        else:
+            return {}
+        padded = np.concatenate([knots, [np.inf, np.inf]])
+        rec = np.zeros((nb + 2, 4))
+        rec[:, 0], rec[:, 1] = padded[base + 1], padded[base + 2]
+        rec[:, 2] = base.astype(np.int64).view(np.float64)                 # int32 in the low word
+        return dict(q_n=nb, q_off=self.add_doubles(rec, dedupe=True, align=2),
+                    q_seg_off=self.add_doubles(seg, align=2), q_nseg=n + 2, q_x0=float(xs[0]),
+                    q_inv=float(inv))
 
     def add_spline(self, ppoly):
         """scipy PPoly/CubicSpline: breakpoints and c[4, n-1] (highest power first)."""
@@ -421,8 +471,13 @@ class StarEngine:
         p = self.params
         U, G, sg, R, sr = tab.composite()
         n = len(U)
-        rows = np.zeros((n, 6))
-        rows[:, 0], rows[:, 1], rows[:, 2], rows[:, 3], rows[:, 4] = U, G, sg, R, sr
+        # mag_b(u) = fma(slope_b, u, a_b): the intercepts are folded in extended precision
+        ld = np.longdouble
+        rows = np.zeros((n, 4))
+        rows[:, 0] = (ld(1) * G - ld(1) * sg * U).astype(np.float64)
+        rows[:, 1] = sg
+        rows[:, 2] = (ld(1) * R - ld(1) * sr * U).astype(np.float64)
+        rows[:, 3] = sr
         thr = np.concatenate([U[1:], [np.inf]])               # pass from row k to k+1
         edges = np.searchsorted(thr[:-1], np.arange(ISO_LUT + 1) / ISO_LUT, side="right")
         lo, k = edges[:-1].astype(np.int64), np.diff(edges).astype(np.int64)

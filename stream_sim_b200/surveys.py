@@ -48,6 +48,8 @@ class TabulatedFunction:
             setattr(f, k, v)
         f.xmin, f.xmax = -np.inf, np.inf
         f.p[0] = self.fill_value
+        for k, v in packer.add_direct_lookup(self.x, self.y, self.fill_value).items():
+            setattr(f, k, v)
         return f
 
     @classmethod
