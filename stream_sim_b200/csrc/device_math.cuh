@@ -690,7 +690,7 @@ __device__ SS_COLD double2 noisy_mag_exact(const SSParams& p, int b, double mt, 
 }
 
 // the double short form, out of line: SS_MATH_FAST's redo inside its guard band
-__device__ SS_COLD double2 noisy_mag_redo(const SSParams& p, int b, double mt, double loge,
+__device__ __noinline__ double2 noisy_mag_redo(const SSParams& p, int b, double mt, double loge,
                                                bool bright, double z) {
   double err, mobs;
   noisy_mag_f64(p, b, mt, loge, bright, z, err, mobs);

@@ -36,6 +36,9 @@
 #ifndef SS_QCURVE
 #define SS_QCURVE 1
 #endif
+#ifndef SS_PREPARE_EARLY
+#define SS_PREPARE_EARLY 1
+#endif
 
 namespace {
 
@@ -166,18 +169,6 @@ struct GridRow {
   double sinx, cosx;  // sin/cos of radians(x)
 };
 
-// thresholds thr[lo .. lo+k-1] lie in one bucket of the u -> step table: guess the step by
-// position inside the bucket, then fix up (one or two trips)
-__device__ __forceinline__ int step_scan(const double* __restrict__ thr, int lo, int k, double u,
-                                         uint32_t lut_n) {
-  const double fb = u * (double)lut_n;
-  int j = lo + (int)((fb - (double)(int)fb) * (double)k);   // candidate: first idx with u < thr[idx]
-  const int hi = lo + k;
-  while (j > lo && u < __ldg(&thr[j - 1])) --j;
-  while (j < hi && u >= __ldg(&thr[j])) ++j;
-  return j;
-}
-
 // 32 bytes per lane in ONE load instruction (LDG.E.ENL2.256, read-only path): the scattered
 // table records cost the L1 data pipe one pass per instruction and lane, whatever the width --
 // the kernel's busiest unit -- so a 64-byte row is fetched as two of these instead of four
@@ -192,6 +183,39 @@ __device__ __forceinline__ Double4 ldg256(const void* p) {
       : "=d"(r.a), "=d"(r.b), "=d"(r.c), "=d"(r.d)
       : "l"(p));
   return r;
+}
+
+// thresholds thr[lo .. lo+k-1] lie in one bucket of the u -> step table: guess the step by
+// position inside the bucket, fetch BOTH neighbouring thresholds of the guess at once (one
+// round trip when the guess is right), then walk if it was not
+__device__ __forceinline__ int step_scan(const double* __restrict__ thr, int lo, int k, double u,
+                                         uint32_t lut_n) {
+  const double fb = u * (double)lut_n;
+  int j = lo + (int)((fb - (double)(int)fb) * (double)k);   // candidate: first idx with u < thr[idx]
+  const int hi = lo + k;
+  const double below = __ldg(&thr[max(j - 1, lo)]), above = __ldg(&thr[min(j, hi - 1)]);
+  if (j > lo && u < below) {
+    --j;
+    while (j > lo && u < __ldg(&thr[j - 1])) --j;
+  } else if (j < hi && u >= above) {
+    ++j;
+    while (j < hi && u >= __ldg(&thr[j])) ++j;
+  }
+  return j;
+}
+
+// One 16-byte entry per bucket of u (SSTables.grid_lut / iso_lut): the step at the bucket's
+// left edge, the number k of thresholds inside the bucket and the first of them.  For k <= 1
+// (82 % of the stars at 2^17 buckets of the phi1 table) the step costs ONE round trip and no
+// loop; fuller buckets finish with the scan.  (Measured: 2^17 buckets beat 2^15 and 2^20;
+// 32-byte entries holding three thresholds cost more in registers than they save in scans.)
+__device__ __forceinline__ int step_from_entry(const double2& e, const double* __restrict__ thr,
+                                               double u, uint32_t lut_n) {
+  const long long packed = __double_as_longlong(e.x);
+  const int lo = (int)(packed & 0xffffffffLL), k = (int)(packed >> 32);
+  int idx = lo + ((k >= 1 && u >= e.y) ? 1 : 0);
+  if (k > 1 && u >= e.y) idx = step_scan(thr, lo, k, u, lut_n);
+  return idx;
 }
 
 __device__ __forceinline__ void load_grid_row(const double* __restrict__ grid_rows, long long idx,
@@ -220,16 +244,9 @@ __device__ __forceinline__ bool grid_sample(const KArgs& a, double u, GridRow& r
     }
     idx = lo;
   } else {
-    // One 16-byte table entry per bucket of u: (first index lo, number k of thresholds
-    // inside the bucket, thr[lo]).  For k <= 1 (82 % of the stars at 2^17 buckets) the
-    // index costs ONE round trip and no loop.  (Measured: 2^17 buckets -- a 2 MB table
-    // that partly lives in L1 -- beat both 2^15 and 2^20.)
     const int b = (int)(u * (double)p.grid_lut_n);
-    const double2 e = __ldg(&reinterpret_cast<const double2*>(a.t.grid_lut)[b]);
-    const long long packed = __double_as_longlong(e.x);
-    const int lo = (int)(packed & 0xffffffffLL), k = (int)(packed >> 32);
-    idx = (k <= 1) ? lo + ((k == 1 && u >= e.y) ? 1 : 0)
-                   : step_scan(a.t.grid_thr, lo, k, u, (uint32_t)p.grid_lut_n);
+    idx = step_from_entry(__ldg(reinterpret_cast<const double2*>(a.t.grid_lut) + b), a.t.grid_thr, u,
+                          (uint32_t)p.grid_lut_n);
   }
   load_grid_row(a.t.grid_rows, idx, row);
   return true;
@@ -297,11 +314,8 @@ __device__ __forceinline__ void iso_sample_direct(const KArgs& a, double u, doub
     idx = p.iso_n - 1;
   } else {
     const int b = (int)(u * (double)p.iso_lut_n);
-    const double2 e = __ldg(&reinterpret_cast<const double2*>(a.t.iso_lut)[b]);
-    const long long packed = __double_as_longlong(e.x);
-    const int lo = (int)(packed & 0xffffffffLL), k = (int)(packed >> 32);
-    idx = (k <= 1) ? lo + ((k == 1 && u >= e.y) ? 1 : 0)
-                   : step_scan(a.t.iso_thr, lo, k, u, (uint32_t)p.iso_lut_n);
+    idx = step_from_entry(__ldg(reinterpret_cast<const double2*>(a.t.iso_lut) + b), a.t.iso_thr, u,
+                          (uint32_t)p.iso_lut_n);
   }
   iso_row_eval(a.t.iso_rows, idx, u, m1, m2);
 }
@@ -689,8 +703,6 @@ k_fused(const __grid_constant__ KArgs a) {
 
   const uint32_t n = (uint32_t)a.n;
   const uint32_t stride = gridDim.x * blockDim.x;
-  const double2* __restrict__ const grid_lut = reinterpret_cast<const double2*>(a.t.grid_lut);
-  const double2* __restrict__ const iso_lut = reinterpret_cast<const double2*>(a.t.iso_lut);
   const uint32_t grid_lut_n = (uint32_t)p.grid_lut_n, iso_lut_n = (uint32_t)p.iso_lut_n;
   const bool z_track = p.track_sampler == SS_SAMPLER_GAUSSIAN;
   const bool z_dist = p.dist_sampler == SS_SAMPLER_GAUSSIAN;
@@ -700,8 +712,8 @@ k_fused(const __grid_constant__ KArgs a) {
   auto prepare = [&](uint32_t star) {
     wp = ss::philox_block(a.offset + star, SS_DRAW_BLOCK_POS, a.keys);
     // bucket = floor(u * buckets), u = w / 2^32, buckets a power of two: the high word of w * buckets
-    eg = __ldg(&grid_lut[__umulhi(wp.x, grid_lut_n)]);
-    ei = __ldg(&iso_lut[__umulhi(wp.y, iso_lut_n)]);
+    eg = __ldg(reinterpret_cast<const double2*>(a.t.grid_lut) + __umulhi(wp.x, grid_lut_n));
+    ei = __ldg(reinterpret_cast<const double2*>(a.t.iso_lut) + __umulhi(wp.y, iso_lut_n));
   };
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) prepare(i);
@@ -710,21 +722,12 @@ k_fused(const __grid_constant__ KArgs a) {
     const double u_phi1 = ss::u32(wp.x), u_mass = ss::u32(wp.y);
     GridRow row;
     {
-      const long long packed = __double_as_longlong(eg.x);
-      const int lo = (int)(packed & 0xffffffffLL), k = (int)(packed >> 32);
-      int idx = lo + ((k == 1 && u_phi1 >= eg.y) ? 1 : 0);
-      if (k > 1) idx = step_scan(a.t.grid_thr, lo, k, u_phi1, grid_lut_n);
+      int idx = step_from_entry(eg, a.t.grid_thr, u_phi1, grid_lut_n);
       idx = (u_phi1 > p.cdf_last) ? p.grid_nthr + 1 : idx;          // interp1d fill_value = 0.0
       load_grid_row(a.t.grid_rows, idx, row);
     }
     double m1, m2;
-    {
-      const long long packed = __double_as_longlong(ei.x);
-      const int lo = (int)(packed & 0xffffffffLL), k = (int)(packed >> 32);
-      int idx = lo + ((k == 1 && u_mass >= ei.y) ? 1 : 0);
-      if (k > 1) idx = step_scan(a.t.iso_thr, lo, k, u_mass, iso_lut_n);
-      iso_row_eval(a.t.iso_rows, idx, u_mass, m1, m2);
-    }
+    iso_row_eval(a.t.iso_rows, step_from_entry(ei, a.t.iso_thr, u_mass, iso_lut_n), u_mass, m1, m2);
     // the two track draws: normals (fp32 Box-Muller) or uniforms, per the samplers
     double n_phi2, n_dist;
     {
@@ -791,6 +794,11 @@ k_fused(const __grid_constant__ KArgs a) {
     ss::ObsOut o;
     ss::observe_star<MATH, SS_QCURVE != 0>(p, tab, share, true, true, mag_g, mag_r, ebv, ml_g, ml_r, z_g,
                                  z_r, ss::u32(wo.z), ss::u32(wo.w), o);
+#if SS_PREPARE_EARLY
+    // the next star's draw block and bucket entries: issued here, so that the column stores
+    // and the counter updates below cover part of their L2 round trip
+    if (i + stride < n) prepare(i + stride);                       // n <= 2^31: no wrap-around
+#endif
     put<OutT>(a.o.mag_obs[SS_BAND_G], i, o.mobs[SS_BAND_G]);
     put<OutT>(a.o.magerr[SS_BAND_G], i, o.err[SS_BAND_G]);
     put<OutT>(a.o.mag_obs[SS_BAND_R], i, o.mobs[SS_BAND_R]);
@@ -801,7 +809,9 @@ k_fused(const __grid_constant__ KArgs a) {
     c_badr_obs += (o.bad[SS_BAND_R] ? 1u : 0u) + (o.observed ? 0x10000u : 0u);
     c_perfect += o.perfect ? 1u : 0u;
 
+#if !SS_PREPARE_EARLY
     if (i + stride < n) prepare(i + stride);                       // n <= 2^31: no wrap-around
+#endif
   }
 
   if (want_cnt) {

@@ -293,6 +293,20 @@ def invcdf_thresholds(cs):
     return out
 
 
+def bucket_lut(thr, buckets):
+    """``SSTables.grid_lut`` / ``iso_lut``: one 16-byte entry per bucket [b, b+1)/buckets of
+    u -- (step at the left edge | thresholds inside << 32, the first of those thresholds).
+    ``thr`` ascending, finite."""
+    thr = np.asarray(thr, dtype=np.float64)
+    edges = np.searchsorted(thr, np.arange(buckets + 1) / buckets, side="right")
+    lo, k = edges[:-1].astype(np.int64), np.diff(edges).astype(np.int64)
+    padded = np.concatenate([thr, [np.inf]])
+    lut = np.empty((buckets, 2), dtype=np.float64)
+    lut[:, 0] = (lo | (k << 32)).view(np.float64)          # two int32 in one double
+    lut[:, 1] = padded[lo]
+    return lut
+
+
 def snr_error_threshold(snr_min=SNR_MIN):
     """Largest magerr e with fl(1/e) >= snr_min: turns the reference's
     ``1.0/magerr >= 5.0`` (observed.py:278-279) into one compare, bit-exactly."""
@@ -479,11 +493,7 @@ class StarEngine:
         rows[:, 2] = (ld(1) * R - ld(1) * sr * U).astype(np.float64)
         rows[:, 3] = sr
         thr = np.concatenate([U[1:], [np.inf]])               # pass from row k to k+1
-        edges = np.searchsorted(thr[:-1], np.arange(ISO_LUT + 1) / ISO_LUT, side="right")
-        lo, k = edges[:-1].astype(np.int64), np.diff(edges).astype(np.int64)
-        lut = np.empty((ISO_LUT, 2))
-        lut[:, 0] = (lo | (k << 32)).view(np.float64)
-        lut[:, 1] = thr[lo]
+        lut = bucket_lut(thr[:-1], ISO_LUT)
         self.iso_rows = torch.from_numpy(rows).to(self.device)
         self.iso_lut = torch.from_numpy(lut).to(self.device)
         self.iso_thr = torch.from_numpy(thr).to(self.device)
@@ -573,11 +583,7 @@ class StarEngine:
         col0 = np.zeros(len(x), dtype=np.int64)
         col0[:] = self.hist_bin("phi1", x).astype(np.int64) & 0xFFFFFFFF
         rows = np.stack([col0.view(np.float64), x, c, s, dc, ds, np.sin(rad), np.cos(rad)], axis=1)
-        edges = np.searchsorted(thr, np.arange(GRID_LUT + 1) / GRID_LUT, side="right")
-        lo, k = edges[:-1].astype(np.int64), np.diff(edges).astype(np.int64)
-        lut = np.empty((GRID_LUT, 2), dtype=np.float64)
-        lut[:, 0] = (lo | (k << 32)).view(np.float64)          # two int32 in one double
-        lut[:, 1] = thr_full[lo]
+        lut = bucket_lut(thr, GRID_LUT)
         self.grid_rows = torch.from_numpy(np.ascontiguousarray(rows, dtype=np.float64)).to(self.device)
         self.grid_lut = torch.from_numpy(lut).to(self.device)
         self.grid_thr = torch.from_numpy(thr_full).to(self.device)
