@@ -43,13 +43,15 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(dtype):
-    """DRAM bytes per star of the star kernel from the committed ncu capture, or None."""
+def kernel_metrics(dtype, math):
+    """Counters of the production kernel from the committed ncu capture (profiles/
+    kernel_metrics.json: DRAM bytes per star, issue-slot and pipe utilisation), or {}.  They
+    are citations of a profile of this kernel, not measurements of this run."""
     try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(dtype)
+        with open(os.path.join(ROOT, "profiles", "kernel_metrics.json")) as f:
+            return json.load(f).get(f"{dtype}_{math}", {})
     except Exception:
-        return None
+        return {}
 
 
 class ClockSampler:
@@ -156,56 +158,88 @@ def cpu_maps(nside):
             for k, kind in (("ebv", "ebv"), ("g", "maglim_g"), ("r", "maglim_r"))}
 
 
-def cpu_throughput(maps, chunk, chunks_per_core, cores, repeats=1):
-    """stars/s of the oracle port over `cores` forked workers."""
+CPU_CHUNK = 1 << 20          # stars per reference-sized call (1e6 .. 1e7)
+
+
+def host_cores():
+    """The cores this process may use (its affinity mask), as a sorted list."""
+    try:
+        return sorted(os.sched_getaffinity(0))
+    except Exception:
+        return list(range(os.cpu_count() or 1))
+
+
+def cpu_steps(maps, chunk, cores, steps, warmup):
+    """Per-step wall times of the oracle port: every step = one `chunk`-star call on each of
+    `cores` forked workers (all cores busy at once, like a user running one process per core)."""
     import multiprocessing as mp
     _cpu_setup(maps)
     ctx = mp.get_context("fork")
-    jobs = [(1000 + i, chunk) for i in range(cores * chunks_per_core)]
-    best = 0.0
+    times = []
     with ctx.Pool(cores) as pool:
-        pool.map(_cpu_chunk, [(1, 1024)] * cores)         # warm the workers
-        for _ in range(repeats):
+        pool.map(_cpu_chunk, [(1, 1024)] * cores)          # fork + import + page in the maps
+        for step in range(warmup + steps):
+            jobs = [(1000 * step + 7 + i, chunk) for i in range(cores)]
             t0 = time.perf_counter()
             pool.map(_cpu_chunk, jobs, chunksize=1)
             dt = time.perf_counter() - t0
-            best = max(best, len(jobs) * chunk / dt)
-    return best, len(jobs) * chunk
+            if step >= warmup:
+                times.append(dt)
+    return times
+
+
+def reference_as_written():
+    """The unmodified reference timed in the build container (scripts/time_reference.py): it
+    cannot run on the GPU box (needs /root/reference), so the committed record is cited."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_reference_as_written.json")) as f:
+            d = json.load(f)
+        return {"value": d["stars_per_s"], "unit": "stars/s", "cores": d["cores"], "kind": "reference",
+                "sample": f"{d['stars']} stars, StreamModel.sample + StreamInjector.inject as written, "
+                          f"nside {d['nside']}, median of {d['repeats']}",
+                "source": "profiles/r02_reference_as_written.json (measured in the build "
+                          "container, not in this run)"}
+    except Exception:
+        return None
+
+
+def cpu_baseline_leg(maps, steps=1, warmup=0):
+    cores = host_cores()
+    times = cpu_steps(maps, CPU_CHUNK, len(cores), steps, warmup)
+    per_step = len(cores) * CPU_CHUNK
+    value = per_step / float(np.median(times))
+    return {"value": value, "unit": "stars/s", "cores": len(cores), "kind": "port",
+            "sample": f"{per_step * len(times)} stars of the same workload ({CPU_CHUNK} per call, one "
+                      f"call per core and step, {len(times)} step(s), median)",
+            "affinity": f"{cores[0]}-{cores[-1]} ({len(cores)} cores)",
+            "per_core": value / len(cores)}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    chunk = 1 << 17
     maps = cpu_maps(NSIDE)
-    _cpu_setup(maps)
-    import multiprocessing as mp
-    ctx = mp.get_context("fork")
-    jobs = [(7 + i, chunk) for i in range(cores)]
-    times = []
-    with ctx.Pool(cores) as pool:
-        for step in range(args.warmup + args.steps):
-            t0 = time.perf_counter()
-            pool.map(_cpu_chunk, [(s + 1000 * step, c) for s, c in jobs], chunksize=1)
-            dt = time.perf_counter() - t0
-            if step >= args.warmup:
-                times.append(dt)
-    per_step = cores * chunk
-    total = sum(times)
-    value = per_step * len(times) / total
+    cores = host_cores()
+    times = cpu_steps(maps, CPU_CHUNK, len(cores), args.steps, max(args.warmup, 1))
+    per_step = len(cores) * CPU_CHUNK
+    med = float(np.median(times))
+    value = per_step / med
     line = {
         "impl": "reference", "metric": "observed stars/sec", "value": value, "unit": "stars/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * med, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "stars_per_step": per_step, "nside": NSIDE,
-                   "note": "CPU arm: NumPy restatement of the reference chain (oracle port); the "
-                           "Python reference needs healpy/astropy/gala/ugali, absent offline"},
-        "cpu_baseline": {"value": value, "unit": "stars/s", "cores": cores, "kind": "port",
-                         "sample": f"{per_step} stars per step ({chunk} per core), "
-                                   f"{args.steps} steps"},
+                   "statistic": "median over steps",
+                   "note": "CPU arm: NumPy restatement of the reference chain (oracle port) on every "
+                           "host core; the Python reference needs healpy/astropy/gala/ugali, absent "
+                           "offline (its as-written timing: cpu_baseline_reference)"},
+        "cpu_baseline": {"value": value, "unit": "stars/s", "cores": len(cores), "kind": "port",
+                         "sample": f"{per_step} stars per step ({CPU_CHUNK} per call and core), "
+                                   f"{args.steps} steps, median",
+                         "affinity": f"{cores[0]}-{cores[-1]} ({len(cores)} cores)"},
+        "cpu_baseline_reference": reference_as_written(),
         "e2e": {"value": value, "unit": "stars/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -317,11 +351,12 @@ def run_gpu(args):
                  "ms_per_step": other_ms, "note": MATH_NOTE[other_math]}
         del eng_m
 
-    # ---- end to end through the C ABI with HOST buffers (pinned), D2H inside
-    n_e2e = min(n, args.e2e_stars)
+    # ---- end to end through the C ABI with HOST buffers (pinned), D2H inside; same stars
+    # per step as the device leg
+    n_e2e = min(n, args.e2e_stars) if args.e2e_stars else n
     if args.no_e2e:
         n_e2e = 1 << 16
-    chunk = min(n_e2e, 1 << 22)
+    chunk = min(n_e2e, args.e2e_chunk)
     host = eng.allocate_host(n_e2e, COLUMNS, dtype)
     ws = eng.host_workspace(chunk, dtype)
     dev_tabs = eng.model_tensors()
@@ -338,7 +373,7 @@ def run_gpu(args):
     e2e_step(0)
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 5))
+    e2e_steps = max(1, min(args.steps, 3))
     for k in range(e2e_steps):
         e2e_step(1 + k)
     barrier()
@@ -347,13 +382,38 @@ def run_gpu(args):
     h2d = sum(h.numel() * h.element_size() for h in host_tabs)
     d2h = n_e2e * bps + 8 * int(host["counters"].numel())
 
+    # ---- what the copies alone can do: the same 12 columns, device -> the same pinned
+    # buffers, one cudaMemcpyAsync per column, (a) this rank alone, (b) all ranks at once
+    def copy_columns():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for c in COLUMNS:
+            host[c].copy_(out[c][:n_e2e], non_blocking=True)
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1) * 1e-3
+
+    copy_columns()
+    alone_s = None
+    for r in range(world):                  # ranks take turns
+        barrier()
+        if r == rank:
+            alone_s = min(copy_columns() for _ in range(2))
+    barrier()
+    together_s = ssd.max_over_ranks(min(copy_columns() for _ in range(2)), device)
+    barrier()
+    alone_gbs = n_e2e * bps / alone_s / 1e9
+    alone_min_gbs = -ssd.max_over_ranks(-alone_gbs, device)
+    ceiling_gbs = world * n_e2e * bps / together_s / 1e9
+
     if world > 1:
         dist.destroy_process_group()
     if rank != 0:
         return
     peak, peak_src = measured_peak()
     achieved = n * bps / (kernel_ms * 1e-3) / 1e9
-    traffic = ncu_traffic(dtype)
+    km = kernel_metrics(dtype, args.math) if args.fused else {}
+    traffic = km.get("dram_bytes_per_star")
     line = {
         "metric": "observed stars/sec", "value": value, "unit": "stars/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
@@ -372,34 +432,121 @@ def run_gpu(args):
                    "observed_fraction": summary["n_observed"] / max(1, summary["n_total"])},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None if traffic is None else traffic * n,
-                     "traffic_source": "profiles/traffic.json (ncu capture of this kernel, bytes per "
-                                       "star x stars per launch; not measured in this run)",
+                     "traffic_source": "profiles/kernel_metrics.json (ncu capture of this kernel: DRAM "
+                                       "bytes per star x stars per launch; a citation, not measured "
+                                       "in this run)",
+                     "issue_frac": km.get("issue_active_frac"),
+                     "fp64_pipe_frac": km.get("fp64_pipe_frac"),
+                     "lsu_data_pipe_frac": km.get("lsu_data_pipe_frac"),
+                     "instructions_per_star": km.get("instructions_per_star"),
+                     "l2_read_hit_rate": km.get("l2_read_hit_rate"),
+                     "profile": km.get("source"),
                      "peak_source": peak_src,
                      "kernel": "k_fused" if args.fused else "k_stars<GENERATE|ROTATE|OBSERVE>",
                      "algorithmic_bytes_per_star": bps, "kernel_ms": kernel_ms},
         "e2e": {"value": e2e_value, "unit": "stars/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "stars_per_step_per_gpu": n_e2e,
+                "steps": e2e_steps, "chunk_stars": chunk,
                 "api": "ss_generate_observe_host (C ABI, pinned host buffers)",
-                    "host_numa_bound": prev_affinity is not None},
+                "gbs": e2e_value * bps / 1e9,
+                "pcie_gbs": alone_min_gbs,
+                "copy_ceiling_gbs": ceiling_gbs,
+                "frac_of_ceiling": e2e_value * bps / 1e9 / ceiling_gbs,
+                "ceiling_note": "plain cudaMemcpyAsync of the same 12 columns into the same pinned "
+                                "buffers: pcie_gbs = slowest rank copying alone, copy_ceiling_gbs = "
+                                "all ranks copying at once (whole job)",
+                "host_numa_bound": prev_affinity is not None},
         "gpu_launches": args.steps,
         "clocks": clocks,
     }
     if other is not None:
         other["roofline_frac"] = (other["value"] / world) * bps / 1e9 / peak
         line["other_math"] = other
-    if world == 1 and not args.no_cpu:
+    if not args.no_cpu:
         if prev_affinity is not None:
             os.sched_setaffinity(0, prev_affinity)      # the CPU arm gets every host core
-        cores = os.cpu_count() or 1
         maps = {k: v.cpu().numpy() for k, v in (("ebv", survey.ebv_map), ("g", survey.maglim_maps["g"]),
                                                 ("r", survey.maglim_maps["r"]))}
-        chunk_cpu = 1 << 17
-        cpu_value, sample = cpu_throughput(maps, chunk_cpu, 2, cores)
-        line["cpu_baseline"] = {"value": cpu_value, "unit": "stars/s", "cores": cores,
-                                "kind": "port",
-                                "sample": f"{sample} stars of the same workload "
-                                          f"({chunk_cpu} per call, {cores} forked workers)"}
+        del eng, survey, out
+        torch.cuda.empty_cache()
+        line["cpu_baseline"] = cpu_baseline_leg(maps, steps=3 if world == 1 else 1)
+        line["cpu_baseline_reference"] = reference_as_written()
     emit(line)
+
+
+# ------------------------------------------------------------------ census (parity at scale)
+def _census_chunk(path):
+    """Worker: the oracle on one chunk of exported draws, compared with the GPU's columns."""
+    import streamsim_oracle as oracle
+    z = np.load(path)
+    draws = {k[2:]: z[k] for k in z.files if k.startswith("d_")}
+    draws["u_phi2"], draws["z_dist"] = draws["z_phi2"], draws["u_dist"]
+    ref = oracle.generate_observe(_CPU["cfg"], _CPU["iso"], _CPU["R"], _CPU["sv"], draws, nside=NSIDE)
+    res = {"n": int(len(z["pix"])),
+           "pix_diff": int((ref["pix"] != z["pix"]).sum()),
+           "flag_diff": int((ref["flag_observed"] != z["flag_observed"].astype(bool)).sum()),
+           "phi1_diff": int((ref["phi1"] != z["phi1"]).sum())}
+    worst = 0.0
+    for k in ("phi2", "dist", "mag_g", "mag_r", "ra", "dec", "mag_g_obs", "mag_r_obs", "magerr_g",
+              "magerr_r"):
+        a, b = z[k], ref[k]
+        nan_a, nan_b = np.isnan(a), np.isnan(b)
+        res.setdefault("nan_pattern_diff", 0)
+        res["nan_pattern_diff"] += int((nan_a != nan_b).sum())
+        ok = ~(nan_a | nan_b)
+        if ok.any():
+            worst = max(worst, float(np.max(np.abs(a[ok] - b[ok]) / np.maximum(np.abs(b[ok]), 1e-300))))
+    res["max_rel_err"] = worst
+    os.unlink(path)
+    return res
+
+
+def run_census(args):
+    """Parity census at BASELINE size: N stars through (1) the production kernel and (2) the
+    generic kernel with its draws exported -- byte-compared on the device -- and (3) the NumPy
+    oracle fed with those draws on all host cores: the COUNT of differing pixel indices and
+    flags (expected 0) is the evidence for the kernel's rewrites of the reference's chain
+    (z = w_z / tt = lon * 2/pi instead of the degree round trip; one log instead of
+    exp10 + log10; SNR cut decided on log10(error))."""
+    import multiprocessing as mp
+    import torch
+    from helpers import LazyMap
+    torch.cuda.set_device(0)
+    device = torch.device("cuda", 0)
+    eng, survey = build_engine(device, NSIDE, math=args.math, fused=1)
+    gen, _ = build_engine(device, NSIDE, survey=survey, math=args.math, fused=0)
+    _cpu_setup(dict(ebv=LazyMap("ebv", NSIDE), g=LazyMap("maglim_g", NSIDE), r=LazyMap("maglim_r", NSIDE)))
+    cores = host_cores()
+    chunk, total = 1 << 22, args.census
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+    ctx = mp.get_context("fork")
+    pending, agg, kernel_diff, t0 = [], [], 0, time.perf_counter()
+    with ctx.Pool(len(cores)) as pool:
+        for lo in range(0, total, chunk):
+            m = min(chunk, total - lo)
+            a = eng.generate_observe(m, seed=args.seed, offset=lo, pix=True)
+            b = gen.generate_observe(m, seed=args.seed, offset=lo, pix=True, export_draws=True)
+            for k in a:
+                kernel_diff += int((a[k].view(torch.uint8) != b[k].view(torch.uint8)).sum())
+            d = gen.exported_draws(b)
+            path = os.path.join(shm, f"ss_census_{os.getpid()}_{lo}.npz")
+            np.savez(path, **{"d_" + k: d[k] for k in ("u_phi1", "z_phi2", "u_dist", "u_mass", "z_r",
+                                                      "z_g", "u_det", "u_det2")},
+                     **{k: v.cpu().numpy() for k, v in a.items()})
+            pending.append(pool.apply_async(_census_chunk, (path,)))
+            while len(pending) > 2 * len(cores):
+                agg.append(pending.pop(0).get())
+        agg += [p.get() for p in pending]
+    out = {"census": {"stars": sum(r["n"] for r in agg), "math": args.math,
+                      "fused_vs_generic_bytes_differing": kernel_diff,
+                      "pix_differing": sum(r["pix_diff"] for r in agg),
+                      "flag_observed_differing": sum(r["flag_diff"] for r in agg),
+                      "phi1_differing": sum(r["phi1_diff"] for r in agg),
+                      "nan_pattern_differing": sum(r["nan_pattern_diff"] for r in agg),
+                      "max_rel_err_float_columns": max(r["max_rel_err"] for r in agg),
+                      "oracle_cores": len(cores), "seconds": time.perf_counter() - t0,
+                      "workload": WORKLOAD, "nside": NSIDE, "seed": args.seed}}
+    emit(out)
 
 
 _RESULT_FD = None
@@ -429,7 +576,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--stars", type=int, default=100_000_000,
                     help="stars per step per GPU (BASELINE config 4: 1e8 stars)")
-    ap.add_argument("--e2e-stars", type=int, default=1 << 24)
+    ap.add_argument("--e2e-stars", type=int, default=0,
+                    help="stars per step per GPU of the end-to-end leg (0 = same as --stars)")
+    ap.add_argument("--e2e-chunk", type=int, default=1 << 22,
+                    help="stars per chunk of the host pipeline (double-buffered)")
     ap.add_argument("--dtype", choices=("f64", "f32"), default="f64")
     ap.add_argument("--seed", type=int, default=12345)
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
@@ -438,6 +588,9 @@ def main():
                     help="arithmetic of the main leg (see MATH_NOTE)")
     ap.add_argument("--no-other-math", action="store_true",
                     help="skip the supplementary leg that times the other arithmetic mode")
+    ap.add_argument("--census", type=int, default=0,
+                    help="instead of timing: run N stars through the production kernel, the generic "
+                         "kernel and the NumPy oracle and print the number of differing pixels/flags")
     ap.add_argument("--fused", type=int, default=1,
                     help="1: production kernel k_fused (default); 0: the generic k_stars")
     ap.add_argument("--no-e2e", action="store_true",
@@ -447,6 +600,8 @@ def main():
         args.warmup = max(args.warmup, 1) if args.impl == "reference" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.census:
+        run_census(args)
     else:
         run_gpu(args)
 
