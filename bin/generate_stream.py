@@ -4,6 +4,8 @@
 Same command line as the reference's bin/generate_stream.py:51-76:
 
     generate_stream.py CONFIG [-o stream_out.csv] [-p] [--seed N]
+
+An output name ending in .parquet / .pq selects the Parquet sink instead of CSV.
 """
 import argparse
 import os
@@ -45,7 +47,10 @@ def main(stream_cls=StreamModel):
     print(f"Reading config: {args.config}")
     stars = generate_stream(parse_config(args.config), stream_cls, args.seed)
     print(f"Writing {args.outfile}")
-    stars.to_csv(args.outfile, index=False)
+    if args.outfile.endswith((".parquet", ".pq")):      # columnar sink (not in the reference)
+        stars.to_parquet(args.outfile, index=False)
+    else:
+        stars.to_csv(args.outfile, index=False)
     if args.plot:
         try:
             import matplotlib
@@ -58,7 +63,7 @@ def main(stream_cls=StreamModel):
         ax.hist2d(stars["phi1"], stars["phi2"], bins=(200, 60))
         ax.set_xlabel("phi1 (deg)")
         ax.set_ylabel("phi2 (deg)")
-        png = args.outfile.replace(".csv", ".png")
+        png = os.path.splitext(args.outfile)[0] + ".png"
         print(f"Writing {png}")
         fig.savefig(png, facecolor="white")
 

@@ -32,7 +32,47 @@ def timed(fn, steps=5, warm=2):
     return e0.elapsed_time(e1) / steps * 1e-3
 
 
+def inject_paths(n=10_000_000):
+    """Wall-clock of StreamInjector.inject through the Python API at n rows, per output mode:
+    how much of a call is host work around the kernel (pandas, object columns, sinks)."""
+    import tempfile
+    import time
+    import numpy as np
+    import pandas as pd
+    from stream_sim_b200.observed import StreamInjector
+    dev = torch.device("cuda", 0)
+    inj = StreamInjector(Survey.synthetic(4096, 4096, device=dev))
+    rng = np.random.default_rng(0)
+    cat = pd.DataFrame(dict(ra=rng.uniform(0, 360, n), dec=np.degrees(np.arcsin(rng.uniform(-1, 1, n))),
+                            mag_g=rng.uniform(17, 29, n), mag_r=rng.uniform(17, 29, n)))
+    tmp = tempfile.mkdtemp()
+    modes = {
+        "pandas, reference layout (BAD_MAG object columns)": dict(),
+        "pandas, bad_mag='nan' (float columns)": dict(bad_mag="nan"),
+        "table (columns stay on the GPU)": dict(output="table"),
+        "arrow": dict(output="arrow"),
+        "parquet (zstd)": dict(output="parquet", path=os.path.join(tmp, "inj.parquet")),
+    }
+    res = {}
+    inj.inject(cat.iloc[:1000], seed=1, verbose=False)             # build the engine, warm up
+    for name, kw in modes.items():
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = inj.inject(cat, seed=1, verbose=False, **kw)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        res[name] = dict(seconds=dt, rows_per_s=n / dt)
+        del out
+    t0 = time.perf_counter()
+    cat.to_csv(os.path.join(tmp, "cat.csv"), index=False)
+    res["(for scale) DataFrame.to_csv of the 4 input columns"] = dict(seconds=time.perf_counter() - t0)
+    return dict(rows=n, modes=res)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "inject":
+        print(json.dumps(inject_paths(int(float(sys.argv[2])) if len(sys.argv) > 2 else 10_000_000), indent=1))
+        return
     n = 1 << 25
     dev = torch.device("cuda", 0)
     frame = GreatCircleFrame.from_endpoints(*NOTEBOOK_ENDPOINTS)

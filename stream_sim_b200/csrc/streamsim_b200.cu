@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -38,6 +39,10 @@
 #endif
 #ifndef SS_PREPARE_EARLY
 #define SS_PREPARE_EARLY 1
+#endif
+// 1: 32-bit integer arithmetic for the RING index of maps up to nside 8192
+#ifndef SS_HP32
+#define SS_HP32 1
 #endif
 
 namespace {
@@ -769,7 +774,12 @@ k_fused(const __grid_constant__ KArgs a) {
     else L = ss::hp_locate(ra, dec);
     double ebv = ss::nan_d(), ml_g = ss::nan_d(), ml_r = ss::nan_d();
     if (L.valid) {
+#if SS_HP32
+      const long long pe = (L.have_sth || p.nside_ebv > 8192) ? ss::hp_ring(L, p.nside_ebv)
+                                                             : (long long)ss::hp_ring32(L.z, L.tt, p.nside_ebv);
+#else
       const long long pe = ss::hp_ring(L, p.nside_ebv);
+#endif
       if (PACKED) {
         const Double4 r = ldg256(a.m.packed + 4 * pe);
         ebv = r.a; ml_g = r.b; ml_r = r.c;
@@ -1021,6 +1031,10 @@ int launch_kernel(K kern, const KArgs& a, int smem, int grid, int block, cudaStr
   int& have = configured.emplace(std::make_pair((const void*)kern, dev), -1).first->second;
   if (smem > have) {
     SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    // experiment knob: share of the unified L1 / shared memory to reserve as shared memory
+    // (percent; unset = the driver's choice)
+    if (const char* c = getenv("SS_SMEM_CARVEOUT"))
+      SS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(c)));
     have = smem;
   }
   kern<<<grid, block, smem, stream>>>(a);

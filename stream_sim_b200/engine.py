@@ -196,6 +196,21 @@ class BlobPacker:
         return d.view(np.uint8)
 
 
+def direct_lookup_eval(blob, q, x):
+    """Host model of the device's direct look-up evaluation (csrc ``q_locate`` / ``q_value``)
+    on a finalized blob: what the production kernel computes for a curve at ``x``."""
+    d = np.asarray(blob).view(np.float64)
+    nb, nseg = q["q_n"], q["q_nseg"]
+    rec = d[q["q_off"]:q["q_off"] + 4 * (nb + 2)].reshape(-1, 4)
+    seg = d[q["q_seg_off"]:q["q_seg_off"] + 4 * nseg].reshape(-1, 4)
+    x = np.asarray(x, dtype=float)
+    with np.errstate(invalid="ignore", over="ignore"):
+        t = np.floor((x - q["q_x0"]) * q["q_inv"])
+        b = np.clip(np.where(np.isnan(t), 0.0, t), -1, nb).astype(np.int64) + 1
+        j = rec[b, 2].copy().view(np.int64).astype(np.int32) + (x >= rec[b, 0]) + (x >= rec[b, 1])
+        return seg[j, 2] * (x - seg[j, 0]) + seg[j, 1]
+
+
 def _rebase(f, base):
     """Shift the blob offsets of an SSFunc packed into the cold region."""
     if f.kind in (_lib.FN_LINEAR, _lib.FN_SPLINE, _lib.FN_SPLINE_PRODUCT):

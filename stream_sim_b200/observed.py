@@ -67,12 +67,23 @@ class StreamInjector:
         mag_g, mag_r`` (if absent), ``mag_<band>_obs, magerr_<band>`` per band in
         ``bands`` order, ``flag_observed`` and, with ``perfect_galstarsep=True``,
         ``flag_perfect_galstarsep``.
+
+        ``output`` (not in the reference): ``"pandas"`` (default) the reference's DataFrame;
+        ``"table"`` a :class:`stream_sim_b200.table.StarTable` whose new columns stay on the
+        GPU until used (no per-row Python objects; bad magnitudes are NaN / nulls);
+        ``"arrow"`` a ``pyarrow.Table``; ``"parquet"`` writes ``path`` and returns it.
         """
         verbose = kwargs.get("verbose", True)
         perfect_galstarsep = kwargs.pop("perfect_galstarsep", False)
         rng_compat = kwargs.pop("rng_compat", False)
         bad_mag = kwargs.pop("bad_mag", "string")
         device = kwargs.pop("device", None)
+        output = kwargs.pop("output", "pandas")
+        path = kwargs.pop("path", None)
+        if output not in ("pandas", "table", "arrow", "parquet"):
+            raise ValueError("output must be 'pandas', 'table', 'arrow' or 'parquet'")
+        if output == "parquet" and not path:
+            raise ValueError("output='parquet' needs path=...")
         data = self._load_data(data)
         seed = kwargs.pop("seed", None)
         rng = np.random.default_rng(seed)
@@ -112,6 +123,8 @@ class StreamInjector:
         out = eng.observe(catalog, seed=_fresh_seed() if seed is None else seed, draws=draws,
                           counters=counters)
         eng.raise_for_counters(eng.summarize(counters))
+        if output != "pandas":
+            return self._columnar_result(data, out, bands, perfect_galstarsep, output, path)
         host = {k: v.cpu().numpy() for k, v in out.items()}
 
         data = data.reset_index(drop=True)
@@ -141,6 +154,27 @@ class StreamInjector:
         if kwargs.get("save"):
             self._save_injected_data(data, kwargs.get("folder", None))
         return data
+
+    @staticmethod
+    def _columnar_result(data, out, bands, perfect_galstarsep, output, path):
+        """The injection as a StarTable: the catalog's columns as they are, the kernel's
+        columns still on the device; same column order as the DataFrame."""
+        from .table import StarTable
+        cols = {c: data[c].to_numpy() for c in data.columns}
+        bad = []
+        for band in bands:
+            cols[f"mag_{band}_obs"] = out[f"mag_{band}_obs"]
+            cols[f"magerr_{band}"] = out[f"magerr_{band}"]
+            bad.append(f"mag_{band}_obs")
+        cols["flag_observed"] = out["flag_observed"]
+        if perfect_galstarsep:
+            cols["flag_perfect_galstarsep"] = out["flag_perfect_galstarsep"]
+        table = StarTable(cols, bad_mag_columns=bad)
+        if output == "table":
+            return table
+        if output == "arrow":
+            return table.to_arrow()
+        return table.to_parquet(path)
 
     def _load_data(self, data):
         if isinstance(data, pd.DataFrame):

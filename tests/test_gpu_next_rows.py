@@ -343,3 +343,38 @@ def test_standalone_noise_and_detection_entry_points(survey):
     free_flag = inj.detect_flag(pix, magr, "r", seed=5)
     assert np.array_equal(free_flag, d["u_det"] <= oracle.get_efficiency(
         sv, "r", magr, sv["maglim_maps"]["r"][pix]))
+
+
+def test_inject_columnar_outputs(survey, tmp_path):
+    """inject(output="table" | "arrow" | "parquet"): same numbers as the reference-layout
+    DataFrame, no object columns, new columns left on the GPU until used."""
+    import pyarrow.parquet as pq
+    import torch
+    from stream_sim_b200.observed import StreamInjector
+    from stream_sim_b200.table import StarTable
+    inj = StreamInjector(survey)
+    n = 50000
+    rng = np.random.default_rng(8)
+    cat = pd.DataFrame(dict(ra=rng.uniform(0, 360, n), dec=np.degrees(np.arcsin(rng.uniform(-1, 1, n))),
+                            mag_g=rng.uniform(16, 30, n), mag_r=rng.uniform(16, 30, n)))
+    ref = inj.inject(cat, seed=3, verbose=False, perfect_galstarsep=True)
+    tab = inj.inject(cat, seed=3, verbose=False, perfect_galstarsep=True, output="table")
+    assert isinstance(tab, StarTable) and tab.columns == list(ref.columns) and len(tab) == n
+    assert isinstance(tab.device_column("mag_r_obs"), torch.Tensor) and tab.device_column("mag_r_obs").is_cuda
+    same = tab.to_pandas()
+    for c in ref.columns:
+        if ref[c].dtype == object:
+            assert (ref[c].astype(str) == same[c].astype(str)).all(), c
+        else:
+            assert np.array_equal(ref[c].to_numpy(), same[c].to_numpy(), equal_nan=True), c
+    bad = (ref["mag_r_obs"] == "BAD_MAG").to_numpy()
+    assert 0 < bad.sum() < n and np.array_equal(np.isnan(tab["mag_r_obs"]), bad)
+    arrow = inj.inject(cat, seed=3, verbose=False, perfect_galstarsep=True, output="arrow")
+    assert arrow.column("mag_r_obs").null_count == int(bad.sum())
+    path = inj.inject(cat, seed=3, verbose=False, perfect_galstarsep=True, output="parquet",
+                      path=str(tmp_path / "inj.parquet"))
+    back = pq.read_table(path).to_pandas()
+    assert np.array_equal(back["flag_observed"].to_numpy(), ref["flag_observed"].to_numpy())
+    assert np.array_equal(back["magerr_g"].to_numpy(), ref["magerr_g"].to_numpy(), equal_nan=True)
+    with pytest.raises(ValueError, match="needs path"):
+        inj.inject(cat, seed=3, verbose=False, output="parquet")

@@ -610,3 +610,75 @@ def test_snr_threshold_on_the_log_error():
         ok = lambda v: 1.0 / np.sqrt((10 ** v) ** 2 + sys_err ** 2) >= 5.0
         assert ok(probe).all() and not ok(above).any(), sys_err
     assert np.isnan(snr_loge_threshold(0.3))          # sys error alone fails the cut
+
+
+def test_direct_lookup_curves_match_interp1d():
+    """The direct look-up form of the survey curves (SSFunc.q_*): its host model equals
+    np.interp with fill values bit for bit -- at random points, at every knot and bucket edge
+    and their neighbouring doubles, outside the table and at NaN."""
+    from stream_sim_b200 import synthetic as syn
+    from stream_sim_b200.engine import BlobPacker, direct_lookup_eval
+
+    def ref(xs, ys, fill, x):
+        out = np.interp(x, xs, ys)
+        out = np.where((x < xs[0]) | (x > xs[-1]), fill, out)
+        return np.where(np.isnan(x), np.nan, out)
+
+    rng = np.random.default_rng(0)
+    err, eff = syn.photo_error_csv_columns(), syn.efficiency_csv_columns()
+    tables = [(err["delta_mag"], err["log_mag_err"], 1.0),
+              (eff["delta_mag"], eff["classification_detection_eff"], 0.0)]
+    for _ in range(10):
+        n = int(rng.integers(2, 150))
+        tables.append((np.sort(rng.uniform(-10, 3, n)), rng.normal(size=n), 0.25))
+    built = 0
+    for xs, ys, fill in tables:
+        pk = BlobPacker()
+        pk.add_doubles(np.zeros(int(rng.integers(0, 3))))          # odd / even starting offsets
+        q = pk.add_direct_lookup(xs, ys, fill)
+        if not q:
+            continue
+        built += 1
+        assert q["q_off"] % 2 == 0 and q["q_seg_off"] % 2 == 0
+        edges = xs[0] + np.arange(q["q_n"] + 1) / q["q_inv"]
+        x = np.concatenate([rng.uniform(xs[0] - 3, xs[-1] + 3, 200000), xs, np.nextafter(xs, np.inf),
+                            np.nextafter(xs, -np.inf), edges, np.nextafter(edges, np.inf),
+                            np.nextafter(edges, -np.inf), [np.nan, -1e300, 1e300]])
+        got, exp = direct_lookup_eval(pk.finalize(), q, x), ref(xs, ys, fill, x)
+        assert np.array_equal(got, exp, equal_nan=True)
+    assert built >= 8
+    assert BlobPacker().add_direct_lookup([0.0, 0.0, 1.0], [1.0, 2.0, 3.0], 0.0) == {}   # duplicate knots
+
+
+def test_star_table_sinks(tmp_path):
+    """StarTable (the columnar result of inject(output="table")) on host arrays: the pandas
+    view in the reference's layout ("BAD_MAG" object columns) and as plain floats, Arrow with
+    nulls, a Parquet round trip and the CSV writer in both flavours."""
+    import pandas as pd
+    import pyarrow.parquet as pq
+    from stream_sim_b200.table import StarTable
+    n = 1000
+    rng = np.random.default_rng(3)
+    mobs = rng.uniform(18, 28, n)
+    mobs[::7] = np.nan
+    t = StarTable(dict(ra=rng.uniform(0, 360, n), mag_r_obs=mobs, magerr_r=rng.uniform(0, 1, n),
+                       flag_observed=(rng.uniform(size=n) < 0.3).astype(np.uint8)),
+                  bad_mag_columns=["mag_r_obs", "not_there"])
+    assert len(t) == n and t.columns == ["ra", "mag_r_obs", "magerr_r", "flag_observed"]
+    df = t.to_pandas()
+    assert df["mag_r_obs"].dtype == object and (df["mag_r_obs"][::7] == "BAD_MAG").all()
+    assert df["flag_observed"].dtype == bool
+    assert float(df["mag_r_obs"][1]) == mobs[1]
+    plain = t.to_pandas(compat=False)
+    assert plain["mag_r_obs"].dtype == np.float64 and np.isnan(plain["mag_r_obs"][0])
+    at = t.to_arrow()
+    assert at.column("mag_r_obs").null_count == len(mobs[::7]) and at.num_rows == n
+    back = pq.read_table(t.to_parquet(str(tmp_path / "t.parquet"))).to_pandas()
+    assert np.array_equal(back["ra"].to_numpy(), t["ra"])
+    assert np.array_equal(np.isnan(back["mag_r_obs"].to_numpy(dtype=float)), np.isnan(mobs))
+    csv = pd.read_csv(t.to_csv(str(tmp_path / "t.csv")))
+    assert (csv["mag_r_obs"][::7] == "BAD_MAG").all() and float(csv["mag_r_obs"][1]) == mobs[1]
+    csv2 = pd.read_csv(t.to_csv(str(tmp_path / "t2.csv"), compat=False), float_precision="round_trip")
+    assert np.isnan(csv2["mag_r_obs"][0]) and csv2["mag_r_obs"][1] == mobs[1]
+    with pytest.raises(ValueError, match="different lengths"):
+        StarTable(dict(a=np.zeros(3), b=np.zeros(4)))
