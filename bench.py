@@ -256,7 +256,19 @@ MATH_NOTE = {
 }
 
 
-def build_engine(device, nside, survey=None, math="f64", fused=1):
+def wholesky_config():
+    """Stress variant: stars spread over the whole sky -- flat density along
+    phi1 in [-180, 180], a 40-degree-wide Gaussian across -- so that every map gather goes to
+    a different part of the 200-million-pixel maps and misses L2."""
+    return dict(density=dict(type="Interpolation", xvals=[-180.0, 180.0], yvals=[1.0, 1.0]),
+                track=dict(center=dict(type="Constant", value=0.0),
+                           spread=dict(type="Constant", value=40.0), sampler="Gaussian"),
+                distance_modulus=dict(center=dict(type="Line", slope=0.0, intercept=16.5),
+                                      spread=dict(type="Constant", value=0.3), sampler="Gaussian"),
+                isochrone=dict(name="synthetic"))
+
+
+def build_engine(device, nside, survey=None, math="f64", fused=1, workload="pal5", packed="auto"):
     from helpers import stream_config
     from stream_sim_b200.engine import StarEngine
     from stream_sim_b200.frames import GreatCircleFrame
@@ -264,9 +276,10 @@ def build_engine(device, nside, survey=None, math="f64", fused=1):
     from stream_sim_b200.surveys import Survey
     from stream_sim_b200.synthetic import NOTEBOOK_ENDPOINTS
     survey = Survey.synthetic(nside, nside, device=device) if survey is None else survey
-    eng = StarEngine(stream=StreamModel(stream_config("pal5")), survey=survey,
+    cfg = wholesky_config() if workload == "wholesky" else stream_config("pal5")
+    eng = StarEngine(stream=StreamModel(cfg), survey=survey,
                      frame=GreatCircleFrame.from_endpoints(*NOTEBOOK_ENDPOINTS), device=device,
-                     nside=nside, hist=True, math=math, fused_kernel=bool(fused))
+                     nside=nside, hist=True, math=math, fused_kernel=bool(fused), packed_maps=packed)
     return eng, survey
 
 
@@ -282,7 +295,9 @@ def run_gpu(args):
     device = torch.device("cuda", local)
     # host buffers of the end-to-end leg on the GPU's own NUMA node
     prev_affinity = ssd.bind_host_to_gpu(local)
-    eng, survey = build_engine(device, NSIDE, math=args.math, fused=args.fused)
+    packed = "auto" if args.packed_maps else False
+    eng, survey = build_engine(device, NSIDE, math=args.math, fused=args.fused,
+                               workload=args.workload, packed=packed)
     n = args.stars
     dtype = args.dtype
     out = eng.allocate(n, COLUMNS, dtype)
@@ -322,6 +337,7 @@ def run_gpu(args):
     total_ms = ssd.max_over_ranks(ev[0].elapsed_time(ev[1]), device)
     kernel_ms = float(np.mean([ev[2 + 2 * k].elapsed_time(ev[3 + 2 * k]) for k in range(args.steps)]))
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    eng_packed = bool(eng.maps.packed)
     value = world * n * args.steps / (total_ms * 1e-3)
     total = ssd.reduce_counters(counters.clone())       # reduce ONCE, into a copy
     summary = eng.summarize(total)
@@ -334,7 +350,8 @@ def run_gpu(args):
     other = None
     if not args.no_other_math:
         other_math = "fast" if args.math == "f64" else "f64"
-        eng_m, _ = build_engine(device, NSIDE, survey=survey, math=other_math, fused=args.fused)
+        eng_m, _ = build_engine(device, NSIDE, survey=survey, math=other_math, fused=args.fused,
+                                workload=args.workload, packed=packed)
         cm = eng_m.new_counters()
         for k in range(3):
             eng_m.generate_observe(n, seed=args.seed, offset=k * n, counters=cm, dtype=dtype, out=out)
@@ -420,8 +437,13 @@ def run_gpu(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": dtype,
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "stars_per_step_per_gpu": n, "nside": NSIDE,
-                   "stream": "config/pal5_config.yaml + synthetic isochrone",
+        "config": {"workload": WORKLOAD if args.workload == "pal5" else
+                   "lsst_injection_nside4096_wholesky_stress", "stars_per_step_per_gpu": n,
+                   "nside": NSIDE,
+                   "stream": "config/pal5_config.yaml + synthetic isochrone" if args.workload == "pal5"
+                   else "stress variant: flat density over phi1 in [-180,180], 40-deg Gaussian width",
+                   "maps": "packed (ebv, maglim_g, maglim_r) records, 32 B per pixel" if bool(eng_packed)
+                   else "three separate float64 maps",
                    "rng": "philox4x32-10 (device)", "seed": args.seed,
                    "math": args.math, "math_note": MATH_NOTE[args.math],
                    "l2": "no per-star inputs; outputs (%.1f GB/step) exceed L2 and are "
@@ -591,6 +613,11 @@ def main():
     ap.add_argument("--census", type=int, default=0,
                     help="instead of timing: run N stars through the production kernel, the generic "
                          "kernel and the NumPy oracle and print the number of differing pixels/flags")
+    ap.add_argument("--workload", choices=("pal5", "wholesky"), default="pal5",
+                    help="pal5 = the BASELINE configuration (default); wholesky = the gather stress "
+                         "variant of SURVEY 8d (supplementary, never the headline)")
+    ap.add_argument("--packed-maps", type=int, default=1,
+                    help="1: interleaved (ebv, maglim_g, maglim_r) map records (default); 0: separate maps")
     ap.add_argument("--fused", type=int, default=1,
                     help="1: production kernel k_fused (default); 0: the generic k_stars")
     ap.add_argument("--no-e2e", action="store_true",

@@ -44,6 +44,10 @@
 #ifndef SS_HP32
 #define SS_HP32 1
 #endif
+// 1: k_fused writes pairs of fp64 columns with 128-bit stores (lane-pair exchange)
+#ifndef SS_VEC_STORES
+#define SS_VEC_STORES 0
+#endif
 
 namespace {
 
@@ -74,6 +78,7 @@ struct KArgs {
   // histogram origins / inverse bin widths rounded to fp32
   ss::PhiloxKeys keys;
   float hist_lo[SS_N_HIST], hist_inv[SS_N_HIST];
+  int vec_ok;   // every floating-point column is 16-byte aligned (paired 128-bit stores)
 };
 
 // ---------------------------------------------------------------- smem staging
@@ -124,6 +129,25 @@ __device__ __forceinline__ void stage_blob(void* dst, const void* src, uint32_t 
 template <typename T>
 __device__ __forceinline__ void put(void* col, unsigned long long i, double v) {
   if (col) reinterpret_cast<T*>(col)[i] = (T)v;
+}
+
+// Two columns, one 16-byte store per lane: neighbouring lanes swap one value each (even lanes
+// end up with column A of both stars, odd lanes with column B), so a warp writes its 2 x 256
+// bytes as 32 STG.E.128 instead of 64 STG.E.64.  `full` = the whole warp is inside the range
+// (warp-uniform); the ragged last warp and fp32 columns take the scalar stores.
+template <typename OutT>
+__device__ __forceinline__ void put2(void* ca, void* cb, unsigned long long i, double va, double vb,
+                                     bool full) {
+  if (sizeof(OutT) == 8 && full && ca && cb) {
+    const bool odd = (threadIdx.x & 1) != 0;
+    const double recv = __shfl_xor_sync(0xffffffffu, odd ? va : vb, 1);
+    const double2 v = odd ? make_double2(recv, vb) : make_double2(va, recv);
+    double* const col = reinterpret_cast<double*>(odd ? cb : ca);
+    *reinterpret_cast<double2*>(col + (i & ~1ULL)) = v;
+  } else {
+    put<OutT>(ca, i, va);
+    put<OutT>(cb, i, vb);
+  }
 }
 
 // centre and spread of a TrackModel at x (reference model.py:517-518)
@@ -746,10 +770,16 @@ k_fused(const __grid_constant__ KArgs a) {
     const double dist = track_draw(row.dc, row.ds, p.dist_sampler, n_dist, c_dom);
     if (c_dom && want_cnt) atomicAdd(&s_cnt[SS_CNT_DOMAIN], c_dom);
     const double mag_g = __dadd_rn(m1, dist), mag_r = __dadd_rn(m2, dist);
+#if SS_VEC_STORES
+    const bool full = a.vec_ok && (i | 31u) < n;                   // warp-uniform
+    put2<OutT>(a.o.phi1, a.o.phi2, i, row.x, phi2, full);
+    put2<OutT>(a.o.dist, a.o.mag[SS_BAND_G], i, dist, mag_g, full);
+#else
     put<OutT>(a.o.phi1, i, row.x);
     put<OutT>(a.o.phi2, i, phi2);
     put<OutT>(a.o.dist, i, dist);
     put<OutT>(a.o.mag[SS_BAND_G], i, mag_g);
+#endif
     put<OutT>(a.o.mag[SS_BAND_R], i, mag_r);
     if (HIST) {
       const int b0 = __double2loint(row.thr);                        // host-binned phi1
@@ -765,8 +795,12 @@ k_fused(const __grid_constant__ KArgs a) {
     // ------------------------------------------------ rotate (observed.py:573)
     double wx, wy, wz, lon, ra, dec;
     rotate_star(p, row.sinx, row.cosx, phi2, wx, wy, wz, lon, ra, dec);
+#if SS_VEC_STORES
+    put2<OutT>(a.o.ra, a.o.dec, i, ra, dec, full);
+#else
     put<OutT>(a.o.ra, i, ra);
     put<OutT>(a.o.dec, i, dec);
+#endif
 
     // ------------------------------------------------ observe (observed.py:146-291)
     ss::HpLoc L;
@@ -809,10 +843,15 @@ k_fused(const __grid_constant__ KArgs a) {
     // and the counter updates below cover part of their L2 round trip
     if (i + stride < n) prepare(i + stride);                       // n <= 2^31: no wrap-around
 #endif
+#if SS_VEC_STORES
+    put2<OutT>(a.o.mag_obs[SS_BAND_G], a.o.magerr[SS_BAND_G], i, o.mobs[SS_BAND_G], o.err[SS_BAND_G], full);
+    put2<OutT>(a.o.mag_obs[SS_BAND_R], a.o.magerr[SS_BAND_R], i, o.mobs[SS_BAND_R], o.err[SS_BAND_R], full);
+#else
     put<OutT>(a.o.mag_obs[SS_BAND_G], i, o.mobs[SS_BAND_G]);
     put<OutT>(a.o.magerr[SS_BAND_G], i, o.err[SS_BAND_G]);
     put<OutT>(a.o.mag_obs[SS_BAND_R], i, o.mobs[SS_BAND_R]);
     put<OutT>(a.o.magerr[SS_BAND_R], i, o.err[SS_BAND_R]);
+#endif
     if (a.o.flag_observed) a.o.flag_observed[i] = o.observed ? 1 : 0;
     if (a.o.flag_perfect) a.o.flag_perfect[i] = o.perfect ? 1 : 0;
     c_unseen_badg += (o.unseen ? 1u : 0u) + (o.bad[SS_BAND_G] ? 0x10000u : 0u);
@@ -1287,6 +1326,13 @@ int ss_run(uint32_t stages, const SSParams* p, const SSTables* t, const SSMaps* 
   for (int h = 0; h < SS_N_HIST; ++h) {
     a.hist_lo[h] = (float)p->hist_lo[h];
     a.hist_inv[h] = (float)p->hist_inv_width[h];
+  }
+  {
+    const void* cols[11] = {out->phi1, out->phi2, out->dist, out->mag[0], out->mag[1], out->ra, out->dec,
+                            out->mag_obs[0], out->mag_obs[1], out->magerr[0], out->magerr[1]};
+    uintptr_t bits = 0;
+    for (const void* c : cols) bits |= (uintptr_t)c;
+    a.vec_ok = (bits & 15) == 0;
   }
   int smem, grid;
   if (a.t.blob_hot_bytes <= 0 || a.t.blob_hot_bytes > a.t.blob_bytes)

@@ -682,3 +682,93 @@ def test_star_table_sinks(tmp_path):
     assert np.isnan(csv2["mag_r_obs"][0]) and csv2["mag_r_obs"][1] == mobs[1]
     with pytest.raises(ValueError, match="different lengths"):
         StarTable(dict(a=np.zeros(3), b=np.zeros(4)))
+
+
+def _fits_card(key, value=None, comment=""):
+    """One 80-character header card, laid out by hand from the FITS standard (v4.0 section 4.2):
+    keyword in columns 1-8, '= ' in 9-10, fixed-format values right-justified to column 30,
+    strings quoted from column 11 and padded to at least 8 characters."""
+    if value is None:
+        return f"{key:<8}".ljust(80).encode("ascii")
+    if isinstance(value, bool):
+        field = f"{'T' if value else 'F':>20}"
+    elif isinstance(value, int):
+        field = f"{value:>20d}"
+    else:
+        field = "'" + f"{value:<8}" + "'"
+        field = f"{field:<20}"
+    text = f"{key:<8}= {field}" + (f" / {comment}" if comment else "")
+    assert len(text) <= 80
+    return text.ljust(80).encode("ascii")
+
+
+def _fits_block(cards):
+    raw = b"".join(cards) + _fits_card("END")
+    return raw + b" " * (-len(raw) % 2880)
+
+
+def test_healpix_fits_file_built_from_the_standard(tmp_path):
+    """A HEALPix FITS map assembled byte by byte from the FITS standard, the way healpy's
+    write_map lays it out (primary HDU without data, one BINTABLE with 1024 big-endian
+    float32 values per row, PIXTYPE/ORDERING/NSIDE/INDXSCHM cards) -- nothing of
+    stream_sim_b200.fitsio's own writer is involved -- is read back value for value, in RING
+    and NESTED order; likewise a partial-sky file with an EXPLICIT pixel index column."""
+    import struct
+    from stream_sim_b200 import fitsio, healpix as hp
+    from stream_sim_b200.surveys import SurveyFactory
+    nside = 16
+    npix = 12 * nside * nside
+    values = (np.arange(npix, dtype=np.float32) * np.float32(0.25) - np.float32(100.0))
+    values[5] = np.float32(hp.UNSEEN)
+    primary = _fits_block([_fits_card("SIMPLE", True, "conforms to FITS standard"),
+                           _fits_card("BITPIX", 8, "array data type"),
+                           _fits_card("NAXIS", 0, "number of array dimensions"),
+                           _fits_card("EXTEND", True)])
+    per_row = 1024
+    table_hdr = _fits_block([
+        _fits_card("XTENSION", "BINTABLE", "binary table extension"),
+        _fits_card("BITPIX", 8, "array data type"), _fits_card("NAXIS", 2),
+        _fits_card("NAXIS1", 4 * per_row, "length of dimension 1"),
+        _fits_card("NAXIS2", npix // per_row, "length of dimension 2"),
+        _fits_card("PCOUNT", 0), _fits_card("GCOUNT", 1), _fits_card("TFIELDS", 1),
+        _fits_card("TTYPE1", "TEMPERATURE", "Temperature map"), _fits_card("TFORM1", "1024E"),
+        _fits_card("TUNIT1", "mag"),
+        _fits_card("PIXTYPE", "HEALPIX", "HEALPIX pixelisation"),
+        _fits_card("ORDERING", "NESTED", "Pixel ordering scheme, either RING or NESTED"),
+        _fits_card("COMMENT"),                                     # a blank commentary card
+        _fits_card("NSIDE", nside, "Resolution parameter of HEALPIX"),
+        _fits_card("FIRSTPIX", 0), _fits_card("LASTPIX", npix - 1),
+        _fits_card("INDXSCHM", "IMPLICIT", "Indexing: IMPLICIT or EXPLICIT"),
+        _fits_card("OBJECT", "FULLSKY", "Sky coverage, either FULLSKY or PARTIAL")])
+    data = struct.pack(f">{npix}f", *values.tolist())
+    data += b"\\0" * (-len(data) % 2880)
+    path = str(tmp_path / "by_hand.fits")
+    with open(path, "wb") as f:
+        f.write(primary + table_hdr + data)
+    nest = fitsio.read_healpix_map(path, nest=True)
+    assert nest.dtype == np.float64 and np.array_equal(nest, values.astype(np.float64))
+    ring = fitsio.read_healpix_map(path)
+    assert np.array_equal(ring, hp.reorder_nest_to_ring(values.astype(np.float64)))
+    loaded = SurveyFactory.read_map(path)        # FITS maps come back as hp.read_map gives them
+    assert np.array_equal(loaded, ring) and loaded[hp.ring2nest(nside, np.arange(npix)) == 5][0] < -1e30
+
+    # partial sky: EXPLICIT indexing, columns PIXEL (32-bit integer) and SIGNAL (float64), RING
+    pix = np.array([3, 77, 1000, npix - 1], dtype=np.int32)
+    sig = np.array([21.5, 22.25, -3.0, 1e-3])
+    hdr = _fits_block([
+        _fits_card("XTENSION", "BINTABLE"), _fits_card("BITPIX", 8), _fits_card("NAXIS", 2),
+        _fits_card("NAXIS1", 12), _fits_card("NAXIS2", len(pix)), _fits_card("PCOUNT", 0),
+        _fits_card("GCOUNT", 1), _fits_card("TFIELDS", 2),
+        _fits_card("TTYPE1", "PIXEL"), _fits_card("TFORM1", "1J"),
+        _fits_card("TTYPE2", "SIGNAL"), _fits_card("TFORM2", "1D"),
+        _fits_card("PIXTYPE", "HEALPIX"), _fits_card("ORDERING", "RING"),
+        _fits_card("NSIDE", nside), _fits_card("INDXSCHM", "EXPLICIT"),
+        _fits_card("OBJECT", "PARTIAL")])
+    rows = b"".join(struct.pack(">id", int(p), float(s)) for p, s in zip(pix, sig))
+    rows += b"\\0" * (-len(rows) % 2880)
+    path2 = str(tmp_path / "partial.fits")
+    with open(path2, "wb") as f:
+        f.write(primary + hdr + rows)
+    part = fitsio.read_healpix_map(path2)
+    assert part.size == npix and np.array_equal(part[pix], sig)
+    assert (part == hp.UNSEEN).sum() == npix - len(pix)
