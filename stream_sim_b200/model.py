@@ -23,19 +23,20 @@ _ALL_COLUMNS = ("phi1", "phi2", "dist", "mag_g", "mag_r", "mu1", "mu2", "rv")
 
 
 class ConfigurableModel(object):
-    """Base class: deep-copies ``config``, applies keyword overrides, builds."""
+    """Common base of the model pieces: owns a private copy of its ``config`` section with the
+    keyword overrides merged in, and builds itself from it (``None`` = an absent section:
+    nothing is built).  Same contract as the reference's base class (model.py:25-41)."""
 
     def __init__(self, config, **kwargs):
-        self._config = copy.deepcopy(config)
+        self._config = None if config is None else {**copy.deepcopy(config), **kwargs}
         if self._config is not None:
-            self._config.update(**kwargs)
             self._create_model()
 
     def _create_model(self):
-        pass
+        """Build the sub-models from ``self._config`` (subclasses)."""
 
     def sample(self, size):
-        pass
+        """Draw ``size`` values (subclasses)."""
 
 
 class _Parts:
@@ -244,26 +245,30 @@ class StreamModel(ConfigurableModel):
             print(msg)
 
     def _open_catalog(self, catalog, size=None, inplace=False):
-        """Normalise the input to a DataFrame (reference model.py:386-437)."""
-        src_path = None
-        if catalog is None:
+        """Whatever the caller handed over -> (DataFrame with canonical column names, CSV path
+        it came from or None).  Accepted, as in the reference (model.py:386-437): nothing
+        (``size`` empty rows), a CSV path, a DataFrame (copied unless ``inplace``), a dict of
+        columns.  A table without rows is replaced by ``size`` empty rows."""
+        def blank():
             if size is None:
-                raise ValueError("size must be provided when catalog is None")
-            df = pd.DataFrame(index=np.arange(int(size)))
-        elif isinstance(catalog, str):
-            src_path = catalog
-            df = pd.read_csv(catalog)
-        elif isinstance(catalog, pd.DataFrame):
-            df = catalog if inplace else catalog.copy()
+                raise ValueError("size must be provided when catalog is None" if catalog is None
+                                 else "Empty catalog; provide size")
+            return pd.DataFrame(index=np.arange(int(size)))
+
+        origin = catalog if isinstance(catalog, str) else None
+        if catalog is None:
+            table = blank()
+        elif origin is not None:
+            table = pd.read_csv(origin)
         elif isinstance(catalog, dict):
-            df = pd.DataFrame(catalog)
+            table = pd.DataFrame(catalog)
+        elif isinstance(catalog, pd.DataFrame):
+            table = catalog if inplace else catalog.copy()
         else:
             raise TypeError("catalog must be None, path, DataFrame, or dict")
-        if len(df) == 0:
-            if size is None:
-                raise ValueError("Empty catalog; provide size")
-            df = pd.DataFrame(index=np.arange(int(size)))
-        return self._standardize_columns_name(df), src_path
+        if not len(table):
+            table = blank()
+        return self._standardize_columns_name(table), origin
 
     _ALIASES = {
         "dist": ("dist", "distance", "distance_modulus"),

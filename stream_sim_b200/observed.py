@@ -37,14 +37,13 @@ class StreamInjector:
     mask_cache = {}
 
     def __init__(self, survey, **kwargs):
-        if isinstance(survey, str):
-            self.survey = Survey.load(survey=survey, **kwargs)
-        elif isinstance(survey, Survey):
-            self.survey = survey
-        else:
+        """``survey``: a ready :class:`Survey`, or the name of one to load (keywords go to
+        ``Survey.load``), as in the reference (observed.py:38-46)."""
+        if not isinstance(survey, (str, Survey)):
             raise ValueError("survey must be a string or Survey instance.")
-        self._last_gc_frame = None
-        self._engines = {}
+        self.survey = Survey.load(survey=survey, **kwargs) if isinstance(survey, str) else survey
+        self._last_gc_frame = None       # what gc_frame="last" refers to
+        self._engines = {}               # device engines, one per injection configuration
 
     # ------------------------------------------------------------------ engine cache
     def _engine(self, bands, nside, dust_correction, perfect_galstarsep, detection_mag_cut,
@@ -251,19 +250,21 @@ class StreamInjector:
         import ctypes as C
         import torch
         from .engine import StarEngine, require_device
-        if rng is None:
-            rng = np.random.default_rng(seed)
-        if mask is None:
-            healpix_mask = self._create_mask(mask_type, verbose=verbose)
-        else:
-            healpix_mask = mask
-            if verbose:
-                print("Using provided HEALPix mask for footprint checking.")
-        if healpix_mask is None:
-            if verbose:
-                print("No mask available, returning a random great circle frame.")
+        say = print if verbose else (lambda *a, **k: None)
+        rng = np.random.default_rng(seed) if rng is None else rng
+
+        def random_frame():              # two endpoints = 4 scalars of the stream, in this order
             return GreatCircleFrame.from_endpoints(self._random_uniform_skycoord(rng),
                                                    self._random_uniform_skycoord(rng))
+
+        if mask is not None:
+            say("Using provided HEALPix mask for footprint checking.")
+            healpix_mask = mask
+        else:
+            healpix_mask = self._create_mask(mask_type, verbose=verbose)
+        if healpix_mask is None:         # nothing to test against: any frame will do
+            say("No mask available, returning a random great circle frame.")
+            return random_frame()
         if phi1 is None or phi2 is None:
             raise ValueError("phi1 and phi2 must be provided if no mask is given.")
         device = require_device(device)
@@ -281,8 +282,7 @@ class StreamInjector:
         trials = 0
         while trials < max_iter:
             trials += 1
-            frame = GreatCircleFrame.from_endpoints(self._random_uniform_skycoord(rng),
-                                                    self._random_uniform_skycoord(rng))
+            frame = random_frame()
             eng.set_frame(frame)
             counters.zero_()
             with torch.cuda.device(device):
@@ -314,23 +314,22 @@ class StreamInjector:
     def _create_mask(self, mask_type, verbose=True, ebv_threshold=0.2):
         """Boolean sky mask combining footprint / depth / dust cuts at the coarsest
         resolution involved, cached per (survey, types, threshold) (reference :720-861)."""
+        say = print if verbose else (lambda *a, **k: None)
         if mask_type is None:
-            if verbose:
-                print("⚠ No mask_type provided to build mask.")
+            say("⚠ No mask_type provided to build mask.")
             return None
-        if isinstance(mask_type, str):
-            mask_type = [mask_type]
-        elif not isinstance(mask_type, list):
+        if not isinstance(mask_type, (str, list)):
             raise ValueError("mask_type must be a string, list of strings, or None.")
-        mask_type = sorted(mask_type)
+        # one canonical spelling per combination, so that ["ebv", "footprint"] and
+        # ["footprint", "ebv"] share a cache entry; the dust threshold only matters with "ebv"
+        mask_type = sorted([mask_type] if isinstance(mask_type, str) else mask_type)
         key = (getattr(self.survey, "name", "unknown"), tuple(mask_type),
                ebv_threshold if "ebv" in mask_type else None)
-        if key in self.mask_cache:
-            if verbose:
-                print(f"✓ Using cached mask for {mask_type}")
-            return self.mask_cache[key]
-        if verbose:
-            print(f"Building new mask for {mask_type}...")
+        cached = self.mask_cache.get(key)
+        if cached is not None:
+            say(f"✓ Using cached mask for {mask_type}")
+            return cached
+        say(f"Building new mask for {mask_type}...")
 
         def host(m):
             return m.cpu().numpy() if hasattr(m, "cpu") else np.asarray(m)
