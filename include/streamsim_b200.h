@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SS_ABI_VERSION 13
+#define SS_ABI_VERSION 14
 
 /* error codes */
 #define SS_OK 0
@@ -221,6 +221,9 @@ typedef struct SSParams {
   int32_t grid_nthr;        /* SS_DENSITY_GRID: thresholds (= steps - 1) of the u -> index map */
   int32_t fused_kernel;     /* 1 (default): the production launch may take the pipelined kernel
                                k_fused; 0: always the generic k_stars (tests compare the two) */
+  int32_t grid_wlut_n;      /* buckets of SSTables.grid_wlut (power of two; 0 = absent)  */
+  int32_t iso_wlut_n;       /* buckets of SSTables.iso_wlut  (power of two; 0 = absent)  */
+  int32_t pad2_;
 } SSParams;
 
 typedef struct SSTables {
@@ -255,6 +258,22 @@ typedef struct SSTables {
   const double* iso_rows;
   const double* iso_lut;
   const double* iso_thr;
+  /* The same two step functions for a 32-BIT draw u = w * 2^-32 (the Philox path), in
+   * integer form: thr[k] <= u  <=>  w >= ceil(thr[k] * 2^32)  <=>  w > wthr[k] with
+   * wthr[k] = ceil(thr[k] * 2^32) - 1 (0xFFFFFFFF = never; thresholds <= 0 are folded into the
+   * first bucket's step), so a step is decided by integer compares and three thresholds fit
+   * in one 16-byte bucket entry:
+   *   wlut[wlut_n][4 x uint32] = (lo | min(k, 4095) << 20, t0, t1, t2): lo = step at the bucket's
+   *   left edge (< 2^20), k = thresholds inside the bucket, t0..t2 = the first three of them
+   *   (0xFFFFFFFF where there is none): step = lo + (w > t0) + (w > t1) + (w > t2), complete for
+   *   k <= 3; fuller buckets finish on wthr[lo + 3 .. lo + k) (all of wthr[lo + 3 ..) when k
+   *   saturates at 4095).  bucket = w >> (32 - log2 wlut_n).
+   * grid_wthr[grid_nthr], iso_wthr[iso_n - 1].  Optional (SSParams.grid_wlut_n / iso_wlut_n
+   * = 0: absent); the pipelined production kernel requires both. */
+  const uint32_t* grid_wlut;
+  const uint32_t* grid_wthr;
+  const uint32_t* iso_wlut;
+  const uint32_t* iso_wthr;
 } SSTables;
 
 typedef struct SSMaps {

@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 # ---- constants mirrored from the header
 STAGE_GENERATE, STAGE_ROTATE, STAGE_OBSERVE = 1, 2, 4
@@ -65,13 +65,15 @@ class SSParams(C.Structure):
         ("photo_error", SSFunc), ("completeness", SSFunc), ("detection", SSFunc),
         ("hist_enable", _i32), ("grid_lut_n", _i32),
         ("hist_lo", _f64 * N_HIST), ("hist_inv_width", _f64 * N_HIST),
-        ("math_mode", _i32), ("iso_lut_n", _i32), ("grid_nthr", _i32), ("fused_kernel", _i32)]
+        ("math_mode", _i32), ("iso_lut_n", _i32), ("grid_nthr", _i32), ("fused_kernel", _i32),
+        ("grid_wlut_n", _i32), ("iso_wlut_n", _i32), ("pad2_", _i32)]
 
 
 class SSTables(C.Structure):
     _fields_ = [("blob", _vp), ("blob_bytes", _i64), ("blob_hot_bytes", _i64), ("cdf_pairs", _vp), ("cdf_perm", _vp),
                 ("grid", _vp), ("grid_rows", _vp), ("grid_lut", _vp), ("grid_thr", _vp),
-                ("iso_rows", _vp), ("iso_lut", _vp), ("iso_thr", _vp)]
+                ("iso_rows", _vp), ("iso_lut", _vp), ("iso_thr", _vp),
+                ("grid_wlut", _vp), ("grid_wthr", _vp), ("iso_wlut", _vp), ("iso_wthr", _vp)]
 
 
 class SSMaps(C.Structure):

@@ -37,8 +37,11 @@
 #ifndef SS_QCURVE
 #define SS_QCURVE 1
 #endif
-#ifndef SS_PREPARE_EARLY
-#define SS_PREPARE_EARLY 1
+// where k_fused starts on the next star's draw block and bucket entries: 0 = end of the
+// iteration, 1 = before the observe stores, 2 = right behind the map gather (its Philox
+// block then runs while the gather is in flight)
+#ifndef SS_PREP_POS
+#define SS_PREP_POS 2
 #endif
 // 1: 32-bit integer arithmetic for the RING index of maps up to nside 8192
 #ifndef SS_HP32
@@ -48,8 +51,29 @@
 #ifndef SS_VEC_STORES
 #define SS_VEC_STORES 0
 #endif
+// 1: k_fused stages the next star's draw block and bucket entries in shared memory with
+// cp.async (no registers in flight); 0: plain loads into registers at the end of an iteration
+#ifndef SS_ASYNC_PREP
+#define SS_ASYNC_PREP 1
+#endif
+// 1: k_fused computes the star's OBS draw block (flux-noise normals, Bernoulli words) right
+// behind the row loads of the generate stage, so that it runs while they are in flight
+#ifndef SS_OBS_EARLY
+#define SS_OBS_EARLY 1
+#endif
+// 1: k_fused reads the survey curves through eight bank-group-private copies of their
+// look-up records (ss::QRep), built in shared memory by each CTA.  Measured: the copies take
+// the shared-memory bank conflicts of the curve look-ups away (2.2 of 9.4 data-pipe passes
+// per star) and the kernel gets 5 % SLOWER (95 KB less L1 for the table gathers, 4 more
+// registers): the L1TEX data pipe is not what bounds it.  Off.
+#ifndef SS_QREP
+#define SS_QREP 0
+#endif
 
 namespace {
+
+// k_fused's dynamic shared memory behind the blob: three 16-byte staging slots per thread
+constexpr int kFusedStage = SS_ASYNC_PREP ? 3 * 16 * SS_FUSED_BLOCK : 0;
 
 thread_local char g_err[512] = "";
 
@@ -79,6 +103,7 @@ struct KArgs {
   ss::PhiloxKeys keys;
   float hist_lo[SS_N_HIST], hist_inv[SS_N_HIST];
   int vec_ok;   // every floating-point column is 16-byte aligned (paired 128-bit stores)
+  int grid_wshift, iso_wshift;   // bucket of a word table = w >> shift
 };
 
 // ---------------------------------------------------------------- smem staging
@@ -245,6 +270,31 @@ __device__ __forceinline__ int step_from_entry(const double2& e, const double* _
   int idx = lo + ((k >= 1 && u >= e.y) ? 1 : 0);
   if (k > 1 && u >= e.y) idx = step_scan(thr, lo, k, u, lut_n);
   return idx;
+}
+
+// The same look-up for a 32-bit draw, in integers (SSTables.grid_wlut / iso_wlut): the entry
+// holds the step at the bucket's left edge and the first three thresholds inside it, as words;
+// fuller buckets (0.1 % of the draws at 2^18 buckets of the Pal 5 table) finish with a binary
+// search on the word thresholds.
+__device__ __forceinline__ int step_from_words(const uint4& e, const uint32_t* __restrict__ wthr,
+                                               uint32_t w, int nthr) {
+  const int lo = (int)(e.x & 0xFFFFFu);
+  int idx = lo + (w > e.y ? 1 : 0) + (w > e.z ? 1 : 0) + (w > e.w ? 1 : 0);
+  const int k = (int)(e.x >> 20);
+  if (k > 3 && w > e.w) {
+    int a = lo + 3, b = (k == 4095) ? nthr : lo + k;
+    while (a < b) {
+      const int mid = (a + b) >> 1;
+      if (w > __ldg(&wthr[mid])) a = mid + 1; else b = mid;
+    }
+    idx = a;
+  }
+  return idx;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src)
+               : "memory");
 }
 
 __device__ __forceinline__ void load_grid_row(const double* __restrict__ grid_rows, long long idx,
@@ -692,6 +742,35 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
   }
 }
 
+// Where the bank-group-private copies of the curve records live (ss::QRep), in 16-byte
+// chunks from the start of their region: per curve (photo error, completeness, detection)
+// the (x_a, x_b) halves of its q_n + 2 bucket records and the (x_j, f_j) halves of its q_nseg
+// segment records, eight copies each; curves sharing a table share the copies.
+struct QRepLayout {
+  int rec[3], seg[3];
+  int chunks;
+};
+
+__host__ __device__ inline QRepLayout qrep_layout(const SSParams& p) {
+  const SSFunc* f[3] = {&p.photo_error, &p.completeness, &p.detection};
+  const int ncurves = p.perfect_galstarsep ? 3 : 2;
+  QRepLayout L;
+  L.chunks = 0;
+  for (int c = 0; c < 3; ++c) {
+    L.rec[c] = L.seg[c] = 0;
+    if (c >= ncurves) continue;
+    L.rec[c] = -1;
+    L.seg[c] = -1;
+    for (int d = 0; d < c; ++d) {
+      if (f[d]->q_off == f[c]->q_off && f[d]->q_n == f[c]->q_n) L.rec[c] = L.rec[d];
+      if (f[d]->q_seg_off == f[c]->q_seg_off && f[d]->q_nseg == f[c]->q_nseg) L.seg[c] = L.seg[d];
+    }
+    if (L.rec[c] < 0) { L.rec[c] = L.chunks; L.chunks += 8 * (f[c]->q_n + 2); }
+    if (L.seg[c] < 0) { L.seg[c] = L.chunks; L.chunks += 8 * f[c]->q_nseg; }
+  }
+  return L;
+}
+
 // k_fused: the production kernel -- free-running generate -> rotate -> observe with the
 // phi1 grid table, the composite isochrone table, both bands, RING maps and the survey
 // curves in shared memory (the launcher checks all of that; anything else runs k_stars).
@@ -729,42 +808,98 @@ k_fused(const __grid_constant__ KArgs a) {
   stage_blob(smem_blob, a.t.blob, a.blob_bytes, &s_bar);
   const double* const tab = reinterpret_cast<const double*>(smem_blob);
   __syncthreads();
+#if SS_QREP
+  ss::QRep qrep;
+  {
+    const QRepLayout L = qrep_layout(p);
+    double2* const region = reinterpret_cast<double2*>(smem_blob + a.blob_bytes + kFusedStage);
+    const SSFunc* f[3] = {&p.photo_error, &p.completeness, &p.detection};
+    const int ncurves = p.perfect_galstarsep ? 3 : 2;
+    for (int c = 0; c < ncurves; ++c) {
+      bool first_rec = true, first_seg = true;
+      for (int d = 0; d < c; ++d) {
+        first_rec = first_rec && L.rec[d] != L.rec[c];
+        first_seg = first_seg && L.seg[d] != L.seg[c];
+      }
+      // record r of a table is two 16-byte halves; copy k of its first half goes to chunk 8 r + k
+      const double2* const rsrc = reinterpret_cast<const double2*>(tab + f[c]->q_off);
+      const double2* const ssrc = reinterpret_cast<const double2*>(tab + f[c]->q_seg_off);
+      if (first_rec)
+        for (int k = threadIdx.x; k < 8 * (f[c]->q_n + 2); k += blockDim.x) region[L.rec[c] + k] = rsrc[2 * (k >> 3)];
+      if (first_seg)
+        for (int k = threadIdx.x; k < 8 * f[c]->q_nseg; k += blockDim.x) region[L.seg[c] + k] = ssrc[2 * (k >> 3)];
+    }
+    qrep.lane = region + (threadIdx.x & 7);
+    for (int c = 0; c < 3; ++c) {
+      qrep.rec[c] = L.rec[c];
+      qrep.seg[c] = L.seg[c];
+    }
+  }
+  __syncthreads();
+#endif
 
   const uint32_t n = (uint32_t)a.n;
   const uint32_t stride = gridDim.x * blockDim.x;
-  const uint32_t grid_lut_n = (uint32_t)p.grid_lut_n, iso_lut_n = (uint32_t)p.iso_lut_n;
   const bool z_track = p.track_sampler == SS_SAMPLER_GAUSSIAN;
   const bool z_dist = p.dist_sampler == SS_SAMPLER_GAUSSIAN;
 
-  uint4 wp = make_uint4(0u, 0u, 0u, 0u);
-  double2 eg = make_double2(0.0, 0.0), ei = make_double2(0.0, 0.0);
+  const uint4* __restrict__ const glut = reinterpret_cast<const uint4*>(a.t.grid_wlut);
+  const uint4* __restrict__ const ilut = reinterpret_cast<const uint4*>(a.t.iso_wlut);
+  const int gshift = a.grid_wshift, ishift = a.iso_wshift;
+  uint4 wp = make_uint4(0u, 0u, 0u, 0u), eg = wp, ei = wp;
+#if SS_ASYNC_PREP
+  // this thread's three 16-byte staging slots behind the blob (conflict-free: slot k of
+  // thread t at 16 * (k * blockDim + t))
+  uint4* const stg = reinterpret_cast<uint4*>(smem_blob + a.blob_bytes) + threadIdx.x;
   auto prepare = [&](uint32_t star) {
-    wp = ss::philox_block(a.offset + star, SS_DRAW_BLOCK_POS, a.keys);
-    // bucket = floor(u * buckets), u = w / 2^32, buckets a power of two: the high word of w * buckets
-    eg = __ldg(reinterpret_cast<const double2*>(a.t.grid_lut) + __umulhi(wp.x, grid_lut_n));
-    ei = __ldg(reinterpret_cast<const double2*>(a.t.iso_lut) + __umulhi(wp.y, iso_lut_n));
+    const uint4 w = ss::philox_block_c<SS_DRAW_BLOCK_POS>(a.offset + star, a.keys);
+    stg[0] = w;
+    cp_async16(stg + SS_FUSED_BLOCK, glut + (w.x >> gshift));
+    cp_async16(stg + 2 * SS_FUSED_BLOCK, ilut + (w.y >> ishift));
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
+#else
+  auto prepare = [&](uint32_t star) {
+    wp = ss::philox_block_c<SS_DRAW_BLOCK_POS>(a.offset + star, a.keys);
+    eg = __ldg(glut + (wp.x >> gshift));
+    ei = __ldg(ilut + (wp.y >> ishift));
+  };
+#endif
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) prepare(i);
   for (; i < n; i += stride) {
+#if SS_ASYNC_PREP
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    wp = stg[0];
+    eg = stg[SS_FUSED_BLOCK];
+    ei = stg[2 * SS_FUSED_BLOCK];
+#endif
     // ------------------------------------------------ generate (model.py:106-157)
-    const double u_phi1 = ss::u32(wp.x), u_mass = ss::u32(wp.y);
+    const double u_mass = ss::u32(wp.y);
+    // both steps first, then the three row loads back to back, then work that needs none of
+    // them; the empty asm keeps every loaded register alive up to that point -- otherwise the
+    // register allocator hands the unused high word of row.thr to the code in between, whose
+    // first write then waits for the load (a write-after-write hazard on a load in flight)
+    const long long sg = step_from_words(eg, a.t.grid_wthr, wp.x, p.grid_nthr);
+    const long long si = step_from_words(ei, a.t.iso_wthr, wp.y, p.iso_n - 1);
+    const Double4 g0 = ldg256(a.t.grid_rows + 8 * sg), g1 = ldg256(a.t.grid_rows + 8 * sg + 4);
+    const Double4 ri = ldg256(a.t.iso_rows + 4 * si);
+#if SS_OBS_EARLY
+    const uint4 wo = ss::philox_block_c<SS_DRAW_BLOCK_OBS>(a.offset + i, a.keys);
+    float zf_r, zf_g;
+    ss::bm32f(wo.x, wo.y, zf_r, zf_g);
+#endif
+    float zf0 = 0.0f, zf1 = 0.0f;
+    if (z_track || z_dist) ss::bm32f(wp.z, wp.w, zf0, zf1);
+    asm volatile("" ::"d"(g0.a), "d"(g0.b), "d"(g0.c), "d"(g0.d), "d"(g1.a), "d"(g1.b), "d"(g1.c),
+                 "d"(g1.d), "d"(ri.a), "d"(ri.b), "d"(ri.c), "d"(ri.d));
     GridRow row;
-    {
-      int idx = step_from_entry(eg, a.t.grid_thr, u_phi1, grid_lut_n);
-      idx = (u_phi1 > p.cdf_last) ? p.grid_nthr + 1 : idx;          // interp1d fill_value = 0.0
-      load_grid_row(a.t.grid_rows, idx, row);
-    }
-    double m1, m2;
-    iso_row_eval(a.t.iso_rows, step_from_entry(ei, a.t.iso_thr, u_mass, iso_lut_n), u_mass, m1, m2);
+    row.thr = g0.a; row.x = g0.b; row.c = g0.c; row.s = g0.d;
+    row.dc = g1.a; row.ds = g1.b; row.sinx = g1.c; row.cosx = g1.d;
+    const double m1 = fma(ri.b, u_mass, ri.a), m2 = fma(ri.d, u_mass, ri.c);
     // the two track draws: normals (fp32 Box-Muller) or uniforms, per the samplers
-    double n_phi2, n_dist;
-    {
-      float zf0 = 0.0f, zf1 = 0.0f;
-      if (z_track || z_dist) ss::bm32f(wp.z, wp.w, zf0, zf1);
-      n_phi2 = z_track ? (double)zf0 : ss::u32(wp.z);
-      n_dist = z_dist ? (double)zf1 : ss::u32(wp.w);
-    }
+    const double n_phi2 = z_track ? (double)zf0 : ss::u32(wp.z);
+    const double n_dist = z_dist ? (double)zf1 : ss::u32(wp.w);
     unsigned c_dom = 0;
     const double phi2 = track_draw(row.c, row.s, p.track_sampler, n_phi2, c_dom);
     const double dist = track_draw(row.dc, row.ds, p.dist_sampler, n_dist, c_dom);
@@ -806,7 +941,7 @@ k_fused(const __grid_constant__ KArgs a) {
     ss::HpLoc L;
     if (fabs(wz) < 0.9999 && lon == lon) L = ss::hp_from_vector(wz, lon);
     else L = ss::hp_locate(ra, dec);
-    double ebv = ss::nan_d(), ml_g = ss::nan_d(), ml_r = ss::nan_d();
+    double ebv = ss::nan_d(), ml_g = ss::nan_d(), ml_r = ss::nan_d(), map_pad = 0.0;
     if (L.valid) {
 #if SS_HP32
       const long long pe = (L.have_sth || p.nside_ebv > 8192) ? ss::hp_ring(L, p.nside_ebv)
@@ -816,7 +951,7 @@ k_fused(const __grid_constant__ KArgs a) {
 #endif
       if (PACKED) {
         const Double4 r = ldg256(a.m.packed + 4 * pe);
-        ebv = r.a; ml_g = r.b; ml_r = r.c;
+        ebv = r.a; ml_g = r.b; ml_r = r.c; map_pad = r.d;
       } else {
         ebv = __ldg(&a.m.ebv[pe]);
         const long long pg = (p.nside_maglim[SS_BAND_G] == p.nside_ebv)
@@ -832,16 +967,28 @@ k_fused(const __grid_constant__ KArgs a) {
       if (want_cnt) atomicAdd(&s_cnt[SS_CNT_BADCOORD], 1u);
       if (a.o.pix) a.o.pix[i] = -1;
     }
-    const uint4 wo = ss::philox_block(a.offset + i, SS_DRAW_BLOCK_OBS, a.keys);
+#if SS_PREP_POS == 2
+    if (i + stride < n) prepare(i + stride);                       // n <= 2^31: no wrap-around
+    // (the gathered record stays whole until here: see the row loads above)
+    asm volatile("" ::"d"(ebv), "d"(ml_g), "d"(ml_r), "d"(map_pad));
+#endif
+#if SS_OBS_EARLY
+    const double z_r = (double)zf_r, z_g = (double)zf_g;
+#else
+    const uint4 wo = ss::philox_block_c<SS_DRAW_BLOCK_OBS>(a.offset + i, a.keys);
     double z_r, z_g;
     ss::bm32(wo.x, wo.y, z_r, z_g);
+#endif
     ss::ObsOut o;
+#if SS_QREP
+    ss::observe_star<MATH, 2>(p, tab, share, true, true, mag_g, mag_r, ebv, ml_g, ml_r, z_g, z_r,
+                              ss::u32(wo.z), ss::u32(wo.w), o, &qrep);
+#else
     ss::observe_star<MATH, SS_QCURVE != 0>(p, tab, share, true, true, mag_g, mag_r, ebv, ml_g, ml_r, z_g,
                                  z_r, ss::u32(wo.z), ss::u32(wo.w), o);
-#if SS_PREPARE_EARLY
-    // the next star's draw block and bucket entries: issued here, so that the column stores
-    // and the counter updates below cover part of their L2 round trip
-    if (i + stride < n) prepare(i + stride);                       // n <= 2^31: no wrap-around
+#endif
+#if SS_PREP_POS == 1
+    if (i + stride < n) prepare(i + stride);
 #endif
 #if SS_VEC_STORES
     put2<OutT>(a.o.mag_obs[SS_BAND_G], a.o.magerr[SS_BAND_G], i, o.mobs[SS_BAND_G], o.err[SS_BAND_G], full);
@@ -858,8 +1005,8 @@ k_fused(const __grid_constant__ KArgs a) {
     c_badr_obs += (o.bad[SS_BAND_R] ? 1u : 0u) + (o.observed ? 0x10000u : 0u);
     c_perfect += o.perfect ? 1u : 0u;
 
-#if !SS_PREPARE_EARLY
-    if (i + stride < n) prepare(i + stride);                       // n <= 2^31: no wrap-around
+#if SS_PREP_POS == 0
+    if (i + stride < n) prepare(i + stride);
 #endif
   }
 
@@ -1027,6 +1174,11 @@ ss::PhiloxKeys philox_keys(unsigned long long seed) {
     k0 += 0x9E3779B9u;
     k1 += 0xBB67AE85u;
   }
+  for (uint32_t b = 0; b < 2; ++b) {
+    const unsigned long long m = 0xCD9E8D57ULL * b;
+    K.fold[b][0] = K.rk[0] ^ (uint32_t)(m >> 32);
+    K.fold[b][1] = K.rk[2] ^ (uint32_t)m;
+  }
   return K;
 }
 
@@ -1095,7 +1247,15 @@ bool fused_eligible(const KArgs& a, int smem) {
          !d.u_phi1 && !d.u_mass && !d.n_phi2 && !d.n_dist && !d.z_flux[0] && !d.z_flux[1] &&
          !d.u_det && !d.u_det2 && !a.in.phi1 && !a.in.phi2 && !a.in.dist && !a.o.draws_out &&
          p.photo_error.q_n > 0 && p.completeness.q_n > 0 &&
-         (!p.perfect_galstarsep || p.detection.q_n > 0) && a.n <= (1ULL << 31);
+         (!p.perfect_galstarsep || p.detection.q_n > 0) && a.n <= (1ULL << 31) &&
+         p.grid_wlut_n > 0 && p.iso_wlut_n > 0 && a.t.grid_wlut && a.t.grid_wthr && a.t.iso_wlut &&
+         a.t.iso_wthr;
+}
+
+// dynamic shared memory of k_fused: the hot blob, three 16-byte staging slots per thread (kFusedStage)
+// ... then the bank-group-private copies of the curve records
+int fused_smem(const KArgs& a, int blob_smem) {
+  return blob_smem + kFusedStage + (SS_QREP ? 16 * qrep_layout(a.p).chunks : 0);
 }
 
 template <typename OutT, int MATH, bool HIST>
@@ -1103,8 +1263,9 @@ int launch_fused_p(const KArgs& a, int smem, int grid, cudaStream_t s) {
   const SSParams& p = a.p;
   const bool packed = a.m.packed && a.m.nside_packed == p.nside_ebv &&
                       p.nside_maglim[0] == p.nside_ebv && p.nside_maglim[1] == p.nside_ebv;
-  return packed ? launch_kernel(k_fused<OutT, MATH, HIST, true>, a, smem, grid, SS_FUSED_BLOCK, s)
-                : launch_kernel(k_fused<OutT, MATH, HIST, false>, a, smem, grid, SS_FUSED_BLOCK, s);
+  const int total = fused_smem(a, smem);
+  return packed ? launch_kernel(k_fused<OutT, MATH, HIST, true>, a, total, grid, SS_FUSED_BLOCK, s)
+                : launch_kernel(k_fused<OutT, MATH, HIST, false>, a, total, grid, SS_FUSED_BLOCK, s);
 }
 
 template <typename OutT>
@@ -1136,7 +1297,7 @@ int launch_stage(uint32_t st, const KArgs& a, const DevInfo& d, int smem, int gr
     case 7:
 #endif
       if (fused_eligible(a, smem) &&
-          (SS_FUSED_MIN_CTAS == 1 || SS_FUSED_MIN_CTAS * (smem + kStaticSmem + 1024) <= d.smem_optin))
+          SS_FUSED_MIN_CTAS * (fused_smem(a, smem) + kStaticSmem + 1024) <= d.smem_optin)
         return launch_fused<OutT>(a, d, smem, s);
       return fast ? launch_t<7, OutT, SS_MATH_FAST>(a, smem, grid, s) : launch_t<7, OutT>(a, smem, grid, s);
   }
@@ -1187,6 +1348,9 @@ int validate(uint32_t st, const SSParams* p, const SSTables* t, const SSMaps* m,
       if ((uintptr_t)t->grid_rows & 31) return fail(SS_EINVAL, "grid_rows must be 32-byte aligned%s");
       // u * buckets must be exact for bucket = floor(u * buckets) to agree with the host's edges
       if (p->grid_lut_n & (p->grid_lut_n - 1)) return fail(SS_EINVAL, "grid_lut_n must be a power of two%s");
+      if (p->grid_wlut_n < 0 || (p->grid_wlut_n & (p->grid_wlut_n - 1)) || p->grid_wlut_n == 1 ||
+          (p->grid_wlut_n && (!t->grid_wlut || !t->grid_wthr || ((uintptr_t)t->grid_wlut & 15))))
+        return fail(SS_EINVAL, "grid_wlut_n must be 0 or a power of two >= 2 with 16-byte aligned grid_wlut, grid_wthr%s");
     }
     if (p->density_kind == SS_DENSITY_INVCDF) {
       if (!t->cdf_pairs || p->cdf_n < 2) return fail(SS_EINVAL, "inverse-CDF density needs cdf_pairs%s");
@@ -1201,6 +1365,9 @@ int validate(uint32_t st, const SSParams* p, const SSTables* t, const SSMaps* m,
           return fail(SS_EINVAL, "direct isochrone lookup needs iso_rows, iso_lut, iso_thr%s");
         if ((uintptr_t)t->iso_rows & 31) return fail(SS_EINVAL, "iso_rows must be 32-byte aligned%s");
         if (p->iso_lut_n & (p->iso_lut_n - 1)) return fail(SS_EINVAL, "iso_lut_n must be a power of two%s");
+        if (p->iso_wlut_n < 0 || (p->iso_wlut_n & (p->iso_wlut_n - 1)) || p->iso_wlut_n == 1 ||
+            (p->iso_wlut_n && (!t->iso_wlut || !t->iso_wthr || ((uintptr_t)t->iso_wlut & 15))))
+          return fail(SS_EINVAL, "iso_wlut_n must be 0 or a power of two >= 2 with 16-byte aligned iso_wlut, iso_wthr%s");
       } else {
         if (p->iso_n < 2 || p->imf_n < 2) return fail(SS_EINVAL, "isochrone/IMF tables too short%s");
         if (p->imf_guide_n & (p->imf_guide_n - 1))
@@ -1334,6 +1501,10 @@ int ss_run(uint32_t stages, const SSParams* p, const SSTables* t, const SSMaps* 
     for (const void* c : cols) bits |= (uintptr_t)c;
     a.vec_ok = (bits & 15) == 0;
   }
+  for (int b = p->grid_wlut_n; b > 1; b >>= 1) a.grid_wshift++;    // log2 buckets ...
+  for (int b = p->iso_wlut_n; b > 1; b >>= 1) a.iso_wshift++;
+  a.grid_wshift = 32 - a.grid_wshift;                              // ... -> bucket = w >> shift
+  a.iso_wshift = 32 - a.iso_wshift;
   int smem, grid;
   if (a.t.blob_hot_bytes <= 0 || a.t.blob_hot_bytes > a.t.blob_bytes)
     a.t.blob_hot_bytes = a.t.blob_bytes;

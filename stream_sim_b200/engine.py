@@ -33,6 +33,9 @@ CDF_GUIDE = 8192
 IMF_GUIDE = 4096
 ISO_LUT = 1 << 15
 GRID_LUT = 1 << 17     # measured: 2^17 (2 MB, partly L1-resident) beats 2^15..2^20
+# buckets of the 32-bit word tables (SSTables.grid_wlut / iso_wlut)
+GRID_WLUT = 1 << int(os.environ.get("SS_GRID_WLUT_LOG2", "18"))
+ISO_WLUT = 1 << int(os.environ.get("SS_ISO_WLUT_LOG2", "15"))
 
 
 def _torch():
@@ -322,6 +325,64 @@ def bucket_lut(thr, buckets):
     return lut
 
 
+WLUT_K_CAP = 4095          # k field of a word-table entry saturates here
+WLUT_NEVER = 0xFFFFFFFF
+
+
+def word_thresholds(thr):
+    """A step function's thresholds for a 32-bit draw ``u = w * 2**-32``:
+    ``thr[k] <= u  <=>  w > wthr[k]`` with ``wthr[k] = ceil(thr[k] * 2**32) - 1`` (exact: the
+    scaling is a power of two).  Returns ``(wthr, n_below)``: thresholds at or below zero are
+    passed by every word and are dropped (``n_below`` of them, a constant added to every
+    step); thresholds no word reaches become 0xFFFFFFFF."""
+    thr = np.asarray(thr, dtype=np.float64)
+    if np.any(np.diff(thr) < 0) or np.any(np.isnan(thr)):
+        raise ValueError("thresholds must be ascending")
+    scaled = np.ceil(np.minimum(thr, 2.0) * 4294967296.0)   # integers, exact in double
+    n_below = int(np.count_nonzero(scaled <= 0.0))
+    w = np.clip(scaled[n_below:] - 1.0, 0.0, float(WLUT_NEVER))
+    return w.astype(np.uint32), n_below
+
+
+def bucket_wlut(wthr, n_below, buckets):
+    """``SSTables.grid_wlut`` / ``iso_wlut`` (see the header): one 16-byte entry per bucket of
+    the word, ``(lo | min(k, 4095) << 20, t0, t1, t2)``."""
+    shift = 32 - int(buckets).bit_length() + 1
+    if buckets & (buckets - 1) or not 1 <= buckets <= 1 << 32:
+        raise ValueError("buckets must be a power of two")
+    # w > wthr[k] for every word of buckets >= b  <=>  wthr[k] < b << shift
+    starts = (np.arange(buckets + 1, dtype=np.uint64) << np.uint64(shift))
+    w64 = wthr.astype(np.uint64)
+    edges = np.searchsorted(w64, starts, side="left")     # thresholds passed at the left edge
+    edges[-1] = np.count_nonzero(w64 < WLUT_NEVER)         # 0xFFFFFFFF is never passed
+    lo, k = edges[:-1].astype(np.int64), np.diff(edges).astype(np.int64)
+    if lo.max(initial=0) + n_below >= 1 << 20:
+        raise ValueError("too many steps for a word table")
+    padded = np.concatenate([w64, np.full(3, WLUT_NEVER, dtype=np.uint64)])
+    lut = np.empty((buckets, 4), dtype=np.uint32)
+    lut[:, 0] = ((lo + n_below) | (np.minimum(k, WLUT_K_CAP) << 20)).astype(np.uint32)
+    for c in range(3):
+        lut[:, 1 + c] = np.where(k > c, padded[lo + c], WLUT_NEVER).astype(np.uint32)
+    return lut
+
+
+def wlut_step(lut, wthr, n_below, w):
+    """Host model of the device look-up (csrc ``step_from_words``): the step of word ``w``."""
+    w = np.asarray(w, dtype=np.uint64)
+    buckets = len(lut)
+    shift = 32 - buckets.bit_length() + 1
+    e = lut[(w >> np.uint64(shift)).astype(np.int64)].astype(np.int64)
+    lo, k = e[:, 0] & 0xFFFFF, e[:, 0] >> 20
+    step = lo + (w > e[:, 1]) + (w > e[:, 2]) + (w > e[:, 3])
+    more = (k > 3) & (w > e[:, 3].astype(np.uint64))
+    for i in np.flatnonzero(more):
+        first = int(lo[i]) - n_below + 3                   # index into wthr
+        last = len(wthr) if k[i] == WLUT_K_CAP else int(lo[i]) - n_below + int(k[i])
+        seg = wthr[first:last].astype(np.uint64)
+        step[i] = lo[i] + 3 + np.searchsorted(seg, w[i], side="left")
+    return step
+
+
 def snr_error_threshold(snr_min=SNR_MIN):
     """Largest magerr e with fl(1/e) >= snr_min: turns the reference's
     ``1.0/magerr >= 5.0`` (observed.py:278-279) into one compare, bit-exactly."""
@@ -516,6 +577,7 @@ class StarEngine:
         self.tables.iso_lut = self.iso_lut.data_ptr()
         self.tables.iso_thr = self.iso_thr.data_ptr()
         p.iso_direct, p.iso_n, p.iso_lut_n = 1, n, ISO_LUT
+        self._set_word_table("iso", thr[:-1], ISO_WLUT)
 
 
     def _pack_iso_tables(self, tab, packer):
@@ -607,12 +669,32 @@ class StarEngine:
         self.tables.grid_thr = self.grid_thr.data_ptr()
         self.params.grid_lut_n = GRID_LUT
         self.params.grid_nthr = len(thr)
+        if cs[-1] >= 1.0:                                  # no draw in [0, 1) takes the fill row
+            self._set_word_table("grid", thr, GRID_WLUT)
         self.params.density_kind = _lib.DENSITY_GRID
+
+    def _set_word_table(self, which, thr, buckets):
+        """The 32-bit-word form of a step table (``SSTables.<which>_wlut / _wthr``)."""
+        torch = _torch()
+        try:
+            wthr, n_below = word_thresholds(thr)
+            lut = bucket_wlut(wthr, n_below, buckets)
+        except ValueError:
+            return
+        # indexed by step on the device: the dropped leading thresholds keep their slots
+        full = np.concatenate([np.zeros(n_below, dtype=np.uint32), wthr, np.full(4, WLUT_NEVER, np.uint32)])
+        wl = torch.from_numpy(lut.view(np.int32)).to(self.device)
+        wt = torch.from_numpy(full.view(np.int32)).to(self.device)
+        setattr(self, which + "_wlut", wl)
+        setattr(self, which + "_wthr", wt)
+        setattr(self.tables, which + "_wlut", wl.data_ptr())
+        setattr(self.tables, which + "_wthr", wt.data_ptr())
+        setattr(self.params, which + "_wlut_n", buckets)
 
     def model_tensors(self):
         """Device tensors that make up the model/survey tables (not the maps)."""
         names = ("blob", "cdf_pairs", "cdf_perm", "grid", "grid_rows", "grid_lut", "grid_thr",
-                 "iso_rows", "iso_lut", "iso_thr")
+                 "iso_rows", "iso_lut", "iso_thr", "grid_wlut", "grid_wthr", "iso_wlut", "iso_wthr")
         return [getattr(self, k) for k in names if getattr(self, k, None) is not None]
 
     # ---- rotate

@@ -338,6 +338,47 @@ def test_inverse_cdf_step_function_fuzz():
 
 
 # ------------------------------------------------------------------ configuration + survey schema
+def test_word_tables_reproduce_the_step_function():
+    """engine.word_thresholds / bucket_wlut (SSTables.grid_wlut, iso_wlut): for every 32-bit
+    word w the integer look-up gives #{k : thr[k] <= w * 2**-32}, incl. thresholds at or below
+    zero, at or above one, runs of equal thresholds, buckets fuller than three thresholds and
+    the saturated k field."""
+    from stream_sim_b200.engine import (WLUT_K_CAP, bucket_wlut, invcdf_segments, wlut_step,
+                                        word_thresholds)
+    from stream_sim_b200.model import StreamModel
+    from stream_sim_b200 import samplers as S
+    rng = np.random.default_rng(7)
+
+    def check(thr, buckets):
+        wthr, n_below = word_thresholds(thr)
+        lut = bucket_wlut(wthr, n_below, buckets)
+        shift = 32 - buckets.bit_length() + 1
+        w64 = wthr.astype(np.uint64)
+        cand = np.concatenate([
+            rng.integers(0, 1 << 32, 100000, dtype=np.uint64), w64,
+            np.minimum(w64 + 1, 0xFFFFFFFF), np.maximum(w64.astype(np.int64) - 1, 0).astype(np.uint64),
+            np.array([0, 1, 0xFFFFFFFE, 0xFFFFFFFF], dtype=np.uint64),
+            np.arange(buckets, dtype=np.uint64) << np.uint64(shift)])
+        want = np.searchsorted(thr, cand.astype(np.float64) / 4294967296.0, side="right")
+        assert np.array_equal(wlut_step(lut, wthr, n_below, cand), want)
+        return lut[:, 0] >> 20
+
+    from helpers import stream_config
+    st = StreamModel(stream_config("pal5"))
+    xg, pdf = st.density.density.grid(100000)
+    thr, _ = invcdf_segments(*S.inverse_cdf_tables(xg, pdf))
+    k = check(thr, 1 << 18)
+    assert (k > 3).mean() < 0.01                      # the scan is the rare path
+    k = check(st.isochrone.table.composite()[0][1:], 1 << 15)
+    assert k.max() <= 3                               # the isochrone table never scans
+    check(np.array([-1.0, 0.0, 0.0, 0.25, 0.25, 0.25, 0.25, 0.25, 0.5, 1.0, 1.5, np.inf]), 4)
+    k = check(np.sort(rng.uniform(size=20000)) ** 8, 1 << 8)
+    assert k.max() == WLUT_K_CAP
+    check(np.array([]), 2)
+    with pytest.raises(ValueError):
+        word_thresholds([0.5, 0.25])
+
+
 def test_configs_parse_and_models_build():
     from stream_sim_b200.model import (BackgroundModel, SplineStreamModel, StreamModel,
                                        TrackModel)
