@@ -5,6 +5,7 @@ mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_parity.py -q -x -k "fused or fast_math or lsst_configuration or summary_only or shard or empty_and_tiny or nside_4096" > gpurun_out/${tag}_pytest.log 2>&1; tail -3 gpurun_out/${tag}_pytest.log
 timeout 300 python bench.py --no-cpu --no-e2e --steps 10 > gpurun_out/${tag}_intree.json 2> gpurun_out/${tag}_intree.err
 for lib in build/variants/*.so; do
+  [ -f "$lib" ] || continue
   name=$(basename $lib .so)
   STREAMSIM_B200_LIB=$PWD/$lib timeout 300 python bench.py --no-cpu --no-e2e --no-other-math --steps 10 > gpurun_out/${tag}_${name}.json 2> gpurun_out/${tag}_${name}.err
 done

@@ -278,6 +278,107 @@ __device__ __forceinline__ double atan2_nb(double y, double x) {
   return (y < 0.0) ? -a : a;
 }
 
+// Two-wide forms: the same operations, element by element, as the scalar functions above (so
+// the results are bit-identical), written out side by side so that every polynomial
+// coefficient is fetched from the constant bank once for both elements -- constant loads were
+// 13 % of the production kernel's issued instructions -- and the two chains interleave.
+__device__ __forceinline__ void div_pos2(double a0, double d0, double a1, double d1, double& q0,
+                                         double& q1) {
+  double r0, r1;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(d0));
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r1) : "d"(d1));
+  r0 = fma(fma(-d0, r0, 1.0), r0, r0);
+  r1 = fma(fma(-d1, r1, 1.0), r1, r1);
+  q0 = a0 * r0;
+  q1 = a1 * r1;
+  q0 = fma(fma(-q0, d0, a0), r0, q0);
+  q1 = fma(fma(-q1, d1, a1), r1, q1);
+}
+
+__device__ __forceinline__ void log10_nb2(double t0, double t1, double& o0, double& o1) {
+  int h0 = __double2hiint(t0), h1 = __double2hiint(t1);
+  int e0 = (h0 >> 20) - 1023, e1 = (h1 >> 20) - 1023;
+  h0 = (h0 & 0x000fffff) | 0x3ff00000;
+  h1 = (h1 & 0x000fffff) | 0x3ff00000;
+  const bool up0 = h0 >= 0x3ff6a09f, up1 = h1 >= 0x3ff6a09f;
+  h0 -= up0 ? 0x00100000 : 0;
+  h1 -= up1 ? 0x00100000 : 0;
+  e0 += up0 ? 1 : 0;
+  e1 += up1 ? 1 : 0;
+  const double m0 = __hiloint2double(h0, __double2loint(t0)), m1 = __hiloint2double(h1, __double2loint(t1));
+  double s0, s1;
+  div_pos2(m0 - 1.0, m0 + 1.0, m1 - 1.0, m1 + 1.0, s0, s1);
+  const double a0 = s0 * s0, a1 = s1 * s1, b0 = a0 * a0, b1 = a1 * a1;
+  double pe0 = kLogC[9], po0 = kLogC[10], pe1 = kLogC[9], po1 = kLogC[10];
+#pragma unroll
+  for (int k = 7; k >= 1; k -= 2) {
+    const double ce = kLogC[k], co = kLogC[k + 1];
+    pe0 = fma(pe0, b0, ce); po0 = fma(po0, b0, co);
+    pe1 = fma(pe1, b1, ce); po1 = fma(po1, b1, co);
+  }
+  const double p0 = fma(po0, a0, pe0), p1 = fma(po1, a1, pe1);
+  const double c0 = kLogC[0], l2 = kNum[2];
+  const double lm0 = fma(s0 * a0, p0, s0 * c0), lm1 = fma(s1 * a1, p1, s1 * c0);
+  o0 = fma((double)e0, l2, lm0);
+  o1 = fma((double)e1, l2, lm1);
+}
+
+__device__ __forceinline__ void exp10_nb2(double x0, double x1, double& o0, double& o1) {
+  const double lh = kNum[0], ll = kNum[1], magic = kNum[10];
+  const double t0 = fma(x0, lh, magic), t1 = fma(x1, lh, magic);
+  const int n0 = __double2loint(t0), n1 = __double2loint(t1);
+  const double nd0 = t0 - magic, nd1 = t1 - magic;
+  const double f0 = fma(x0, ll, fma(x0, lh, -nd0)), f1 = fma(x1, ll, fma(x1, lh, -nd1));
+  const double g0 = f0 * f0, g1 = f1 * f1;
+  double pe0 = kExp2C[12], po0 = kExp2C[13], pe1 = kExp2C[12], po1 = kExp2C[13];
+#pragma unroll
+  for (int k = 10; k >= 0; k -= 2) {
+    const double ce = kExp2C[k], co = kExp2C[k + 1];
+    pe0 = fma(pe0, g0, ce); po0 = fma(po0, g0, co);
+    pe1 = fma(pe1, g1, ce); po1 = fma(po1, g1, co);
+  }
+  const double p0 = fma(fma(po0, f0, pe0), f0, 1.0), p1 = fma(fma(po1, f1, pe1), f1, 1.0);
+  o0 = p0 * __hiloint2double((n0 + 1023) << 20, 0);
+  o1 = p1 * __hiloint2double((n1 + 1023) << 20, 0);
+}
+
+// (lon, lat) of a unit vector: atan2(y0, x0) for any signs and atan2(y1, x1) with x1 >= 0
+// (a hypotenuse), max(|x|, |y|) > 0 for both (|w| = 1)
+__device__ __forceinline__ void atan2_nb2(double y0, double x0, double y1, double x1, double& o0,
+                                          double& o1) {
+  const double ax0 = fabs(x0), ay0 = fabs(y0), ay1 = fabs(y1);
+  const bool st0 = ay0 > ax0, st1 = ay1 > x1;
+  const double mx0 = st0 ? ay0 : ax0, mn0 = st0 ? ax0 : ay0;
+  const double mx1 = st1 ? ay1 : x1, mn1 = st1 ? x1 : ay1;
+  double r0, r1;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(mx0));
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r1) : "d"(mx1));
+  const double magic = kNum[10];
+  const double t0 = fma(mn0 * r0, 8.0, magic), t1 = fma(mn1 * r1, 8.0, magic);
+  const int i0 = __double2loint(t0) & 15, i1 = __double2loint(t1) & 15;
+  const double c0 = (t0 - magic) * 0.125, c1 = (t1 - magic) * 0.125;
+  double q0, q1;
+  div_pos2(fma(-c0, mx0, mn0), fma(c0, mn0, mx0), fma(-c1, mx1, mn1), fma(c1, mn1, mx1), q0, q1);
+  const double a0 = q0 * q0, a1 = q1 * q1, b0 = a0 * a0, b1 = a1 * a1;
+  const double k6 = kAtanC[6], k4 = kAtanC[4], k5 = kAtanC[5];
+  double pe0 = fma(k6, b0, k4), po0 = k5, pe1 = fma(k6, b1, k4), po1 = k5;
+#pragma unroll
+  for (int k = 2; k >= 0; k -= 2) {
+    const double ce = kAtanC[k], co = kAtanC[k + 1];
+    pe0 = fma(pe0, b0, ce); po0 = fma(po0, b0, co);
+    pe1 = fma(pe1, b1, ce); po1 = fma(po1, b1, co);
+  }
+  const double p0 = fma(po0, a0, pe0), p1 = fma(po1, a1, pe1);
+  double v0 = kAtanT[2 * i0] + (fma(q0 * a0, p0, q0) + kAtanT[2 * i0 + 1]);
+  double v1 = kAtanT[2 * i1] + (fma(q1 * a1, p1, q1) + kAtanT[2 * i1 + 1]);
+  const double hp = kNum[3], hpl = kNum[4];
+  v0 = st0 ? (hp - v0) + hpl : v0;
+  v1 = st1 ? (hp - v1) + hpl : v1;
+  v0 = (x0 < 0.0) ? (kNum[5] - v0) + kNum[6] : v0;
+  o0 = (y0 < 0.0) ? -v0 : v0;
+  o1 = (y1 < 0.0) ? -v1 : v1;
+}
+
 __device__ SS_COLD double2 sincos_cold(double b) {
   double s, c;
   sincos(b, &s, &c);
@@ -729,6 +830,26 @@ __device__ __forceinline__ void noisy_mag_f64(const SSParams& p, int b, double m
   mobs = (t > 0.0) ? mt - 2.5 * log10_nb(t) : nan_d();
 }
 
+// both bands at once (bit-identical to two noisy_mag_f64 calls)
+__device__ __forceinline__ void noisy_mag_f64x2(const SSParams& p, const double* mt, const double* loge,
+                                                const bool* bright, const double* z, double* err,
+                                                double* mobs) {
+  double s0, s1;
+  exp10_nb2(loge[0], loge[1], s0, s1);
+  const double eb = p.err_bright;
+  s0 = bright[0] ? eb : s0;
+  s1 = bright[1] ? eb : s1;
+  const double y0 = p.sys_error[0], y1 = p.sys_error[1];
+  err[0] = sqrt_nb(__dadd_rn(__dmul_rn(s0, s0), __dmul_rn(y0, y0)));
+  err[1] = sqrt_nb(__dadd_rn(__dmul_rn(s1, s1), __dmul_rn(y1, y1)));
+  const double kf = kNum[11];
+  const double t0 = 1.0 + err[0] * kf * z[0], t1 = 1.0 + err[1] * kf * z[1];
+  double l0, l1;
+  log10_nb2(t0, t1, l0, l1);
+  mobs[0] = (t0 > 0.0) ? mt[0] - 2.5 * l0 : nan_d();
+  mobs[1] = (t1 > 0.0) ? mt[1] - 2.5 * l1 : nan_d();
+}
+
 // exact flux-space noise for magnitudes whose flux under-/overflows the short form, or
 // log-errors outside exp10_nb's domain (observed.py:863-904, :984-1035); rare, out of line.
 // Returns (err, mobs).
@@ -840,7 +961,11 @@ __device__ __forceinline__ void observe_star(const SSParams& p, const double* __
     }
   }
   o.unseen = ml_c != ml_c;
-  if (plain) {
+  if (plain && MATH == SS_MATH_F64 && band_g && band_r) {
+    noisy_mag_f64x2(p, mt2, loge2, bright2, zf2, o.err, o.mobs);
+    good2[0] = o.mobs[0] == o.mobs[0];
+    good2[1] = o.mobs[1] == o.mobs[1];
+  } else if (plain) {
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
       if (MATH == SS_MATH_FAST) {

@@ -70,6 +70,14 @@
 #define SS_QREP 0
 #endif
 
+// what-if builds (development only; results are wrong on purpose): leave one component of
+// k_fused out to measure what it costs.  1 = no map gather, 2 = no column stores, 4 = no
+// histogram / counter updates, 8 = no observe arithmetic, 16 = no rotation, 32 = no row loads,
+// 64 = no bucket entries (steps straight from the words) and half a grid row
+#ifndef SS_WHATIF
+#define SS_WHATIF 0
+#endif
+
 namespace {
 
 // k_fused's dynamic shared memory behind the blob: three 16-byte staging slots per thread
@@ -154,6 +162,15 @@ __device__ __forceinline__ void stage_blob(void* dst, const void* src, uint32_t 
 template <typename T>
 __device__ __forceinline__ void put(void* col, unsigned long long i, double v) {
   if (col) reinterpret_cast<T*>(col)[i] = (T)v;
+}
+
+template <typename T, bool SURE>
+__device__ __forceinline__ void putc(void* col, unsigned long long i, double v) {
+#if SS_WHATIF & 2
+  if (v == 1.2345e-300) reinterpret_cast<T*>(col)[i] = (T)v;
+#else
+  if (SURE || col) reinterpret_cast<T*>(col)[i] = (T)v;
+#endif
 }
 
 // Two columns, one 16-byte store per lane: neighbouring lanes swap one value each (even lanes
@@ -413,8 +430,8 @@ __device__ __forceinline__ void rotate_star(const SSParams& p, double sl, double
   wy = p.R[1] * v0 + p.R[4] * v1 + p.R[7] * v2;
   wz = p.R[2] * v0 + p.R[5] * v1 + p.R[8] * v2;
   const double R2D = ss::kNum[7];
-  lon = ss::atan2_nb(wy, wx);
-  dec = ss::atan2_nb(wz, ss::sqrt_nb(wx * wx + wy * wy)) * R2D;
+  ss::atan2_nb2(wy, wx, wz, ss::sqrt_nb(wx * wx + wy * wy), lon, dec);
+  dec *= R2D;
   ra = lon * R2D;
   ra = (ra < 0.0) ? ra + 360.0 : ra;
 }
@@ -785,7 +802,9 @@ __host__ __device__ inline QRepLayout qrep_layout(const SSParams& p) {
 //     right after the generate stage, before the rotation raises the register pressure;
 //   * PACKED: the three survey maps interleaved as one 32-byte record per pixel -- one
 //     sector per star instead of three.
-template <typename OutT, int MATH, bool HIST, bool PACKED>
+//   * ALLCOLS: every floating-point column and flag_observed are requested (the launcher
+//     checks) -- no per-store NULL tests.
+template <typename OutT, int MATH, bool HIST, bool PACKED, bool ALLCOLS>
 __global__ void __launch_bounds__(SS_FUSED_BLOCK, SS_FUSED_MIN_CTAS)
 k_fused(const __grid_constant__ KArgs a) {
   extern __shared__ __align__(16) unsigned char smem_blob[];
@@ -854,9 +873,11 @@ k_fused(const __grid_constant__ KArgs a) {
   auto prepare = [&](uint32_t star) {
     const uint4 w = ss::philox_block_c<SS_DRAW_BLOCK_POS>(a.offset + star, a.keys);
     stg[0] = w;
+#if !(SS_WHATIF & 64)
     cp_async16(stg + SS_FUSED_BLOCK, glut + (w.x >> gshift));
     cp_async16(stg + 2 * SS_FUSED_BLOCK, ilut + (w.y >> ishift));
     asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
   };
 #else
   auto prepare = [&](uint32_t star) {
@@ -880,10 +901,27 @@ k_fused(const __grid_constant__ KArgs a) {
     // them; the empty asm keeps every loaded register alive up to that point -- otherwise the
     // register allocator hands the unused high word of row.thr to the code in between, whose
     // first write then waits for the load (a write-after-write hazard on a load in flight)
+#if SS_WHATIF & 64
+    const long long sg = ((unsigned long long)wp.x * (unsigned)p.grid_nthr) >> 32;
+    const long long si = ((unsigned long long)wp.y * (unsigned)(p.iso_n - 1)) >> 32;
+#else
     const long long sg = step_from_words(eg, a.t.grid_wthr, wp.x, p.grid_nthr);
     const long long si = step_from_words(ei, a.t.iso_wthr, wp.y, p.iso_n - 1);
+#endif
+#if SS_WHATIF & 32
+    Double4 g0, g1, ri;
+    g0.a = 0.0; g0.b = 1e-4 * (double)sg - 5.0; g0.c = 0.1; g0.d = 0.2; g1.a = 16.5; g1.b = 0.05;
+    g1.c = 1e-5 * (double)sg; g1.d = 1.0 - g1.c; ri.a = 5.0; ri.b = 1e-3 * (double)si; ri.c = 4.5; ri.d = ri.b;
+#else
+#if SS_WHATIF & 64
+    const Double4 g0 = ldg256(a.t.grid_rows + 8 * sg);
+    Double4 g1;
+    g1.a = 16.5 + 0.1 * g0.b; g1.b = 1e-4; g1.c = sin(g0.b * 0.017453292519943295); g1.d = cos(g0.b * 0.017453292519943295);
+#else
     const Double4 g0 = ldg256(a.t.grid_rows + 8 * sg), g1 = ldg256(a.t.grid_rows + 8 * sg + 4);
+#endif
     const Double4 ri = ldg256(a.t.iso_rows + 4 * si);
+#endif
 #if SS_OBS_EARLY
     const uint4 wo = ss::philox_block_c<SS_DRAW_BLOCK_OBS>(a.offset + i, a.keys);
     float zf_r, zf_g;
@@ -910,13 +948,13 @@ k_fused(const __grid_constant__ KArgs a) {
     put2<OutT>(a.o.phi1, a.o.phi2, i, row.x, phi2, full);
     put2<OutT>(a.o.dist, a.o.mag[SS_BAND_G], i, dist, mag_g, full);
 #else
-    put<OutT>(a.o.phi1, i, row.x);
-    put<OutT>(a.o.phi2, i, phi2);
-    put<OutT>(a.o.dist, i, dist);
-    put<OutT>(a.o.mag[SS_BAND_G], i, mag_g);
+    putc<OutT, ALLCOLS>(a.o.phi1, i, row.x);
+    putc<OutT, ALLCOLS>(a.o.phi2, i, phi2);
+    putc<OutT, ALLCOLS>(a.o.dist, i, dist);
+    putc<OutT, ALLCOLS>(a.o.mag[SS_BAND_G], i, mag_g);
 #endif
-    put<OutT>(a.o.mag[SS_BAND_R], i, mag_r);
-    if (HIST) {
+    putc<OutT, ALLCOLS>(a.o.mag[SS_BAND_R], i, mag_r);
+    if (HIST && !(SS_WHATIF & 4)) {
       const int b0 = __double2loint(row.thr);                        // host-binned phi1
       atomicAdd(&s_hist[b0 >= 0 ? b0 : kDump], 1u);
       const float hv[4] = {(float)phi2, (float)dist, (float)mag_g, (float)(mag_g - mag_r)};
@@ -929,12 +967,16 @@ k_fused(const __grid_constant__ KArgs a) {
 
     // ------------------------------------------------ rotate (observed.py:573)
     double wx, wy, wz, lon, ra, dec;
+#if SS_WHATIF & 16
+    wx = row.cosx; wy = row.sinx; wz = phi2 * 0.01; lon = 4.0 + 0.1 * row.sinx; ra = lon * 57.0; dec = wz * 57.0;
+#else
     rotate_star(p, row.sinx, row.cosx, phi2, wx, wy, wz, lon, ra, dec);
+#endif
 #if SS_VEC_STORES
     put2<OutT>(a.o.ra, a.o.dec, i, ra, dec, full);
 #else
-    put<OutT>(a.o.ra, i, ra);
-    put<OutT>(a.o.dec, i, dec);
+    putc<OutT, ALLCOLS>(a.o.ra, i, ra);
+    putc<OutT, ALLCOLS>(a.o.dec, i, dec);
 #endif
 
     // ------------------------------------------------ observe (observed.py:146-291)
@@ -949,7 +991,9 @@ k_fused(const __grid_constant__ KArgs a) {
 #else
       const long long pe = ss::hp_ring(L, p.nside_ebv);
 #endif
-      if (PACKED) {
+      if (SS_WHATIF & 1) {
+        ebv = 0.05 + 1e-9 * (double)(pe & 1023); ml_g = 26.0; ml_r = 25.7;
+      } else if (PACKED) {
         const Double4 r = ldg256(a.m.packed + 4 * pe);
         ebv = r.a; ml_g = r.b; ml_r = r.c; map_pad = r.d;
       } else {
@@ -980,7 +1024,10 @@ k_fused(const __grid_constant__ KArgs a) {
     ss::bm32(wo.x, wo.y, z_r, z_g);
 #endif
     ss::ObsOut o;
-#if SS_QREP
+#if SS_WHATIF & 8
+    o.mobs[0] = mag_g + ebv; o.mobs[1] = mag_r + ml_g; o.err[0] = ml_r; o.err[1] = z_r + z_g;
+    o.observed = wo.z > wo.w; o.perfect = false; o.unseen = false; o.bad[0] = o.bad[1] = false;
+#elif SS_QREP
     ss::observe_star<MATH, 2>(p, tab, share, true, true, mag_g, mag_r, ebv, ml_g, ml_r, z_g, z_r,
                               ss::u32(wo.z), ss::u32(wo.w), o, &qrep);
 #else
@@ -994,12 +1041,12 @@ k_fused(const __grid_constant__ KArgs a) {
     put2<OutT>(a.o.mag_obs[SS_BAND_G], a.o.magerr[SS_BAND_G], i, o.mobs[SS_BAND_G], o.err[SS_BAND_G], full);
     put2<OutT>(a.o.mag_obs[SS_BAND_R], a.o.magerr[SS_BAND_R], i, o.mobs[SS_BAND_R], o.err[SS_BAND_R], full);
 #else
-    put<OutT>(a.o.mag_obs[SS_BAND_G], i, o.mobs[SS_BAND_G]);
-    put<OutT>(a.o.magerr[SS_BAND_G], i, o.err[SS_BAND_G]);
-    put<OutT>(a.o.mag_obs[SS_BAND_R], i, o.mobs[SS_BAND_R]);
-    put<OutT>(a.o.magerr[SS_BAND_R], i, o.err[SS_BAND_R]);
+    putc<OutT, ALLCOLS>(a.o.mag_obs[SS_BAND_G], i, o.mobs[SS_BAND_G]);
+    putc<OutT, ALLCOLS>(a.o.magerr[SS_BAND_G], i, o.err[SS_BAND_G]);
+    putc<OutT, ALLCOLS>(a.o.mag_obs[SS_BAND_R], i, o.mobs[SS_BAND_R]);
+    putc<OutT, ALLCOLS>(a.o.magerr[SS_BAND_R], i, o.err[SS_BAND_R]);
 #endif
-    if (a.o.flag_observed) a.o.flag_observed[i] = o.observed ? 1 : 0;
+    if (ALLCOLS || a.o.flag_observed) a.o.flag_observed[i] = o.observed ? 1 : 0;
     if (a.o.flag_perfect) a.o.flag_perfect[i] = o.perfect ? 1 : 0;
     c_unseen_badg += (o.unseen ? 1u : 0u) + (o.bad[SS_BAND_G] ? 0x10000u : 0u);
     c_badr_obs += (o.bad[SS_BAND_R] ? 1u : 0u) + (o.observed ? 0x10000u : 0u);
@@ -1264,8 +1311,13 @@ int launch_fused_p(const KArgs& a, int smem, int grid, cudaStream_t s) {
   const bool packed = a.m.packed && a.m.nside_packed == p.nside_ebv &&
                       p.nside_maglim[0] == p.nside_ebv && p.nside_maglim[1] == p.nside_ebv;
   const int total = fused_smem(a, smem);
-  return packed ? launch_kernel(k_fused<OutT, MATH, HIST, true>, a, total, grid, SS_FUSED_BLOCK, s)
-                : launch_kernel(k_fused<OutT, MATH, HIST, false>, a, total, grid, SS_FUSED_BLOCK, s);
+  const SSOut& o = a.o;
+  const bool all = o.phi1 && o.phi2 && o.dist && o.mag[0] && o.mag[1] && o.ra && o.dec && o.mag_obs[0] &&
+                   o.mag_obs[1] && o.magerr[0] && o.magerr[1] && o.flag_observed;
+  if (packed && all)
+    return launch_kernel(k_fused<OutT, MATH, HIST, true, true>, a, total, grid, SS_FUSED_BLOCK, s);
+  return packed ? launch_kernel(k_fused<OutT, MATH, HIST, true, false>, a, total, grid, SS_FUSED_BLOCK, s)
+                : launch_kernel(k_fused<OutT, MATH, HIST, false, false>, a, total, grid, SS_FUSED_BLOCK, s);
 }
 
 template <typename OutT>
