@@ -760,47 +760,19 @@ __device__ __forceinline__ double q_value(const SSFunc& f, const double* __restr
   return __dadd_rn(__dmul_rn(slope, __dsub_rn(x, s0.x)), s0.y);
 }
 
-// Bank-group-private copies of the two 16-byte halves every look-up starts with (the production
-// kernel builds them in shared memory): a scattered LDS.128 is served a quarter warp at a
-// time, 8 lanes x 16 bytes on 8 bank groups, and random indices collide (3.3 passes per
-// quarter warp measured on the compact records).  Lane l reads copy l & 7, laid out so that
-// the copy's every chunk sits in bank group l & 7: no conflicts, one pass.
-struct QRep {
-  const double2* lane;     // start of the copies, offset by the lane's bank group
-  int rec[3];              // photo_error, completeness, detection: (x_a, x_b) of bucket b at lane[rec[c] + 8 b]
-  int seg[3];              //                                       (x_j, f_j) of segment j at lane[seg[c] + 8 j]
-};
-
-__device__ __forceinline__ int q_locate_r(const SSFunc& f, const double* __restrict__ tab,
-                                          const double2* __restrict__ rec, double x) {
-  int b = __double2int_rd(__dmul_rn(__dsub_rn(x, f.q_x0), f.q_inv)) + 1;     // NaN -> 1
-  b = max(0, min(b, f.q_n + 1));
-  const double2 r0 = rec[8 * b];
-  const int j = reinterpret_cast<const int*>(tab + f.q_off)[8 * b + 4];
-  return j + (x >= r0.x ? 1 : 0) + (x >= r0.y ? 1 : 0);
-}
-
-__device__ __forceinline__ double q_value_r(const SSFunc& f, const double* __restrict__ tab,
-                                            const double2* __restrict__ seg, int j, double x) {
-  const double2 s0 = seg[8 * j];
-  const double slope = tab[f.q_seg_off + 4 * j + 2];
-  return __dadd_rn(__dmul_rn(slope, __dsub_rn(x, s0.x)), s0.y);
-}
-
 __device__ __forceinline__ double photo_error_log_q(const SSParams& p, const double* __restrict__ tab,
                                                     double sat, double mag, double delta, int j,
-                                                    bool& bright, const double2* seg = nullptr) {
+                                                    bool& bright) {
   bright = mag < sat;
-  const double v = seg ? q_value_r(p.photo_error, tab, seg, j, delta) : q_value(p.photo_error, tab, j, delta);
+  const double v = q_value(p.photo_error, tab, j, delta);
   const double w = (delta <= p.delta_saturation && mag >= sat) ? p.log_err_at_dsat : v;
   return bright ? 0.0 : w;
 }
 
 __device__ __forceinline__ double efficiency_q(const SSParams& p, const SSFunc& f,
                                                const double* __restrict__ tab, double sat,
-                                               double mag, double maglim, double delta, int j,
-                                               const double2* seg = nullptr) {
-  double r = seg ? q_value_r(f, tab, seg, j, delta) : q_value(f, tab, j, delta);
+                                               double mag, double maglim, double delta, int j) {
+  double r = q_value(f, tab, j, delta);
   r = (mag > sat && delta <= p.delta_saturation) ? 1.0 : r;
   r = (mag < sat) ? 0.0 : r;
   return (maglim < sat || maglim != maglim) ? 0.0 : r;
@@ -891,14 +863,13 @@ __device__ __forceinline__ int curve_share(const SSParams& p) {
 }
 
 // QCURVE: the survey curves are read through their direct look-up form (the production
-// kernel; the launcher checks that every curve has one; 2 = through the bank-group-private
-// copies `rep`), else through the guided search.
-template <int MATH, int QCURVE = 0>
+// kernel; the launcher checks that every curve has one), else through the guided search.
+template <int MATH, bool QCURVE = false>
 __device__ __forceinline__ void observe_star(const SSParams& p, const double* __restrict__ tab,
                                              int share, bool band_g, bool band_r, double mag_g,
                                              double mag_r, double ebv, double ml_g, double ml_r,
                                              double z_g, double z_r, double u_det, double u_det2,
-                                             ObsOut& o, const QRep* rep = nullptr) {
+                                             ObsOut& o) {
   // Stage 1: per band, the table look-ups.  Stage 2: the error / noise arithmetic of BOTH
   // bands as one straight-line block, so that the two dependency chains interleave.
   double ext2[2], mt2[2], loge2[2], zf2[2], dl2[2], ml2[2];
@@ -920,10 +891,7 @@ __device__ __forceinline__ void observe_star(const SSParams& p, const double* __
     j2[b] = 0;
     o.err[b] = o.mobs[b] = nan_d();
     if (!have2[b]) continue;
-    if (QCURVE == 2) {
-      j2[b] = q_locate_r(p.photo_error, tab, rep->lane + rep->rec[0], dl2[b]);
-      loge2[b] = photo_error_log_q(p, tab, p.saturation[b], mt2[b], dl2[b], j2[b], bright2[b], rep->lane + rep->seg[0]);
-    } else if (QCURVE) {
+    if (QCURVE) {
       j2[b] = q_locate(p.photo_error, tab, dl2[b]);
       loge2[b] = photo_error_log_q(p, tab, p.saturation[b], mt2[b], dl2[b], j2[b], bright2[b]);
     } else {
@@ -938,14 +906,7 @@ __device__ __forceinline__ void observe_star(const SSParams& p, const double* __
   const double sat_c = cr ? p.saturation[1] : p.saturation[0];
   const int j_p = cr ? j2[1] : j2[0];
   bool flag_c, flag_d = false;
-  if (QCURVE == 2) {
-    const int j_c = (share & 1) ? j_p : q_locate_r(p.completeness, tab, rep->lane + rep->rec[1], dl_c);
-    flag_c = u_det <= efficiency_q(p, p.completeness, tab, sat_c, mt_c, ml_c, dl_c, j_c, rep->lane + rep->seg[1]);
-    if (p.perfect_galstarsep) {
-      const int j_d = (share & 2) ? j_p : q_locate_r(p.detection, tab, rep->lane + rep->rec[2], dl_c);
-      flag_d = u_det2 <= efficiency_q(p, p.detection, tab, sat_c, mt_c, ml_c, dl_c, j_d, rep->lane + rep->seg[2]);
-    }
-  } else if (QCURVE) {
+  if (QCURVE) {
     const int j_c = (share & 1) ? j_p : q_locate(p.completeness, tab, dl_c);
     flag_c = u_det <= efficiency_q(p, p.completeness, tab, sat_c, mt_c, ml_c, dl_c, j_c);
     if (p.perfect_galstarsep) {

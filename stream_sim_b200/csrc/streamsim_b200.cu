@@ -33,41 +33,9 @@
 #ifndef SS_FUSED_MIN_CTAS
 #define SS_FUSED_MIN_CTAS 1
 #endif
-// 1: k_fused reads the survey curves through their direct look-up form (SSFunc.q_*)
-#ifndef SS_QCURVE
-#define SS_QCURVE 1
-#endif
-// where k_fused starts on the next star's draw block and bucket entries: 0 = end of the
-// iteration, 1 = before the observe stores, 2 = right behind the map gather (its Philox
-// block then runs while the gather is in flight)
-#ifndef SS_PREP_POS
-#define SS_PREP_POS 2
-#endif
 // 1: 32-bit integer arithmetic for the RING index of maps up to nside 8192
 #ifndef SS_HP32
 #define SS_HP32 1
-#endif
-// 1: k_fused writes pairs of fp64 columns with 128-bit stores (lane-pair exchange)
-#ifndef SS_VEC_STORES
-#define SS_VEC_STORES 0
-#endif
-// 1: k_fused stages the next star's draw block and bucket entries in shared memory with
-// cp.async (no registers in flight); 0: plain loads into registers at the end of an iteration
-#ifndef SS_ASYNC_PREP
-#define SS_ASYNC_PREP 1
-#endif
-// 1: k_fused computes the star's OBS draw block (flux-noise normals, Bernoulli words) right
-// behind the row loads of the generate stage, so that it runs while they are in flight
-#ifndef SS_OBS_EARLY
-#define SS_OBS_EARLY 1
-#endif
-// 1: k_fused reads the survey curves through eight bank-group-private copies of their
-// look-up records (ss::QRep), built in shared memory by each CTA.  Measured: the copies take
-// the shared-memory bank conflicts of the curve look-ups away (2.2 of 9.4 data-pipe passes
-// per star) and the kernel gets 5 % SLOWER (95 KB less L1 for the table gathers, 4 more
-// registers): the L1TEX data pipe is not what bounds it.  Off.
-#ifndef SS_QREP
-#define SS_QREP 0
 #endif
 
 // what-if builds (development only; results are wrong on purpose): leave one component of
@@ -81,7 +49,7 @@
 namespace {
 
 // k_fused's dynamic shared memory behind the blob: three 16-byte staging slots per thread
-constexpr int kFusedStage = SS_ASYNC_PREP ? 3 * 16 * SS_FUSED_BLOCK : 0;
+constexpr int kFusedStage = 3 * 16 * SS_FUSED_BLOCK;
 
 thread_local char g_err[512] = "";
 
@@ -110,7 +78,6 @@ struct KArgs {
   // histogram origins / inverse bin widths rounded to fp32
   ss::PhiloxKeys keys;
   float hist_lo[SS_N_HIST], hist_inv[SS_N_HIST];
-  int vec_ok;   // every floating-point column is 16-byte aligned (paired 128-bit stores)
   int grid_wshift, iso_wshift;   // bucket of a word table = w >> shift
 };
 
@@ -171,25 +138,6 @@ __device__ __forceinline__ void putc(void* col, unsigned long long i, double v) 
 #else
   if (SURE || col) reinterpret_cast<T*>(col)[i] = (T)v;
 #endif
-}
-
-// Two columns, one 16-byte store per lane: neighbouring lanes swap one value each (even lanes
-// end up with column A of both stars, odd lanes with column B), so a warp writes its 2 x 256
-// bytes as 32 STG.E.128 instead of 64 STG.E.64.  `full` = the whole warp is inside the range
-// (warp-uniform); the ragged last warp and fp32 columns take the scalar stores.
-template <typename OutT>
-__device__ __forceinline__ void put2(void* ca, void* cb, unsigned long long i, double va, double vb,
-                                     bool full) {
-  if (sizeof(OutT) == 8 && full && ca && cb) {
-    const bool odd = (threadIdx.x & 1) != 0;
-    const double recv = __shfl_xor_sync(0xffffffffu, odd ? va : vb, 1);
-    const double2 v = odd ? make_double2(recv, vb) : make_double2(va, recv);
-    double* const col = reinterpret_cast<double*>(odd ? cb : ca);
-    *reinterpret_cast<double2*>(col + (i & ~1ULL)) = v;
-  } else {
-    put<OutT>(ca, i, va);
-    put<OutT>(cb, i, vb);
-  }
 }
 
 // centre and spread of a TrackModel at x (reference model.py:517-518)
@@ -759,35 +707,6 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
   }
 }
 
-// Where the bank-group-private copies of the curve records live (ss::QRep), in 16-byte
-// chunks from the start of their region: per curve (photo error, completeness, detection)
-// the (x_a, x_b) halves of its q_n + 2 bucket records and the (x_j, f_j) halves of its q_nseg
-// segment records, eight copies each; curves sharing a table share the copies.
-struct QRepLayout {
-  int rec[3], seg[3];
-  int chunks;
-};
-
-__host__ __device__ inline QRepLayout qrep_layout(const SSParams& p) {
-  const SSFunc* f[3] = {&p.photo_error, &p.completeness, &p.detection};
-  const int ncurves = p.perfect_galstarsep ? 3 : 2;
-  QRepLayout L;
-  L.chunks = 0;
-  for (int c = 0; c < 3; ++c) {
-    L.rec[c] = L.seg[c] = 0;
-    if (c >= ncurves) continue;
-    L.rec[c] = -1;
-    L.seg[c] = -1;
-    for (int d = 0; d < c; ++d) {
-      if (f[d]->q_off == f[c]->q_off && f[d]->q_n == f[c]->q_n) L.rec[c] = L.rec[d];
-      if (f[d]->q_seg_off == f[c]->q_seg_off && f[d]->q_nseg == f[c]->q_nseg) L.seg[c] = L.seg[d];
-    }
-    if (L.rec[c] < 0) { L.rec[c] = L.chunks; L.chunks += 8 * (f[c]->q_n + 2); }
-    if (L.seg[c] < 0) { L.seg[c] = L.chunks; L.chunks += 8 * f[c]->q_nseg; }
-  }
-  return L;
-}
-
 // k_fused: the production kernel -- free-running generate -> rotate -> observe with the
 // phi1 grid table, the composite isochrone table, both bands, RING maps and the survey
 // curves in shared memory (the launcher checks all of that; anything else runs k_stars).
@@ -795,9 +714,14 @@ __host__ __device__ inline QRepLayout qrep_layout(const SSParams& p) {
 // bytes (tests/test_gpu_parity.py::test_fused_kernel_equals_generic); what differs is the
 // schedule:
 //   * the star index is 32-bit inside a launch (ss_run splits longer ranges);
-//   * the POS Philox block of the NEXT star and its two bucket entries (phi1 table,
-//     isochrone table) are fetched at the end of an iteration, where few registers are
-//     live, so that their L2 round trip is over when the next iteration starts;
+//   * the draws are 32-bit words, so the two step functions (phi1 grid, isochrone) are
+//     decided in integers on the word tables (SSTables.grid_wlut / iso_wlut): one 16-byte
+//     bucket entry with three thresholds settles 99.9 % of the draws without a scan;
+//   * the POS Philox block of the NEXT star is computed right behind the map gather and its
+//     two bucket entries are requested with cp.async into per-thread shared-memory slots (no
+//     registers in flight): their L2 round trip is over when the next iteration starts;
+//   * the three row loads of an iteration are issued back to back and the star's OBS draw
+//     block (Philox + fp32 Box-Muller) runs behind them;
 //   * the phi1 histogram bin comes with the grid row; the other four are binned in fp32
 //     right after the generate stage, before the rotation raises the register pressure;
 //   * PACKED: the three survey maps interleaved as one 32-byte record per pixel -- one
@@ -827,35 +751,6 @@ k_fused(const __grid_constant__ KArgs a) {
   stage_blob(smem_blob, a.t.blob, a.blob_bytes, &s_bar);
   const double* const tab = reinterpret_cast<const double*>(smem_blob);
   __syncthreads();
-#if SS_QREP
-  ss::QRep qrep;
-  {
-    const QRepLayout L = qrep_layout(p);
-    double2* const region = reinterpret_cast<double2*>(smem_blob + a.blob_bytes + kFusedStage);
-    const SSFunc* f[3] = {&p.photo_error, &p.completeness, &p.detection};
-    const int ncurves = p.perfect_galstarsep ? 3 : 2;
-    for (int c = 0; c < ncurves; ++c) {
-      bool first_rec = true, first_seg = true;
-      for (int d = 0; d < c; ++d) {
-        first_rec = first_rec && L.rec[d] != L.rec[c];
-        first_seg = first_seg && L.seg[d] != L.seg[c];
-      }
-      // record r of a table is two 16-byte halves; copy k of its first half goes to chunk 8 r + k
-      const double2* const rsrc = reinterpret_cast<const double2*>(tab + f[c]->q_off);
-      const double2* const ssrc = reinterpret_cast<const double2*>(tab + f[c]->q_seg_off);
-      if (first_rec)
-        for (int k = threadIdx.x; k < 8 * (f[c]->q_n + 2); k += blockDim.x) region[L.rec[c] + k] = rsrc[2 * (k >> 3)];
-      if (first_seg)
-        for (int k = threadIdx.x; k < 8 * f[c]->q_nseg; k += blockDim.x) region[L.seg[c] + k] = ssrc[2 * (k >> 3)];
-    }
-    qrep.lane = region + (threadIdx.x & 7);
-    for (int c = 0; c < 3; ++c) {
-      qrep.rec[c] = L.rec[c];
-      qrep.seg[c] = L.seg[c];
-    }
-  }
-  __syncthreads();
-#endif
 
   const uint32_t n = (uint32_t)a.n;
   const uint32_t stride = gridDim.x * blockDim.x;
@@ -866,7 +761,6 @@ k_fused(const __grid_constant__ KArgs a) {
   const uint4* __restrict__ const ilut = reinterpret_cast<const uint4*>(a.t.iso_wlut);
   const int gshift = a.grid_wshift, ishift = a.iso_wshift;
   uint4 wp = make_uint4(0u, 0u, 0u, 0u), eg = wp, ei = wp;
-#if SS_ASYNC_PREP
   // this thread's three 16-byte staging slots behind the blob (conflict-free: slot k of
   // thread t at 16 * (k * blockDim + t))
   uint4* const stg = reinterpret_cast<uint4*>(smem_blob + a.blob_bytes) + threadIdx.x;
@@ -879,22 +773,13 @@ k_fused(const __grid_constant__ KArgs a) {
     asm volatile("cp.async.commit_group;" ::: "memory");
 #endif
   };
-#else
-  auto prepare = [&](uint32_t star) {
-    wp = ss::philox_block_c<SS_DRAW_BLOCK_POS>(a.offset + star, a.keys);
-    eg = __ldg(glut + (wp.x >> gshift));
-    ei = __ldg(ilut + (wp.y >> ishift));
-  };
-#endif
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) prepare(i);
   for (; i < n; i += stride) {
-#if SS_ASYNC_PREP
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     wp = stg[0];
     eg = stg[SS_FUSED_BLOCK];
     ei = stg[2 * SS_FUSED_BLOCK];
-#endif
     // ------------------------------------------------ generate (model.py:106-157)
     const double u_mass = ss::u32(wp.y);
     // both steps first, then the three row loads back to back, then work that needs none of
@@ -922,11 +807,9 @@ k_fused(const __grid_constant__ KArgs a) {
 #endif
     const Double4 ri = ldg256(a.t.iso_rows + 4 * si);
 #endif
-#if SS_OBS_EARLY
     const uint4 wo = ss::philox_block_c<SS_DRAW_BLOCK_OBS>(a.offset + i, a.keys);
     float zf_r, zf_g;
     ss::bm32f(wo.x, wo.y, zf_r, zf_g);
-#endif
     float zf0 = 0.0f, zf1 = 0.0f;
     if (z_track || z_dist) ss::bm32f(wp.z, wp.w, zf0, zf1);
     asm volatile("" ::"d"(g0.a), "d"(g0.b), "d"(g0.c), "d"(g0.d), "d"(g1.a), "d"(g1.b), "d"(g1.c),
@@ -943,16 +826,10 @@ k_fused(const __grid_constant__ KArgs a) {
     const double dist = track_draw(row.dc, row.ds, p.dist_sampler, n_dist, c_dom);
     if (c_dom && want_cnt) atomicAdd(&s_cnt[SS_CNT_DOMAIN], c_dom);
     const double mag_g = __dadd_rn(m1, dist), mag_r = __dadd_rn(m2, dist);
-#if SS_VEC_STORES
-    const bool full = a.vec_ok && (i | 31u) < n;                   // warp-uniform
-    put2<OutT>(a.o.phi1, a.o.phi2, i, row.x, phi2, full);
-    put2<OutT>(a.o.dist, a.o.mag[SS_BAND_G], i, dist, mag_g, full);
-#else
     putc<OutT, ALLCOLS>(a.o.phi1, i, row.x);
     putc<OutT, ALLCOLS>(a.o.phi2, i, phi2);
     putc<OutT, ALLCOLS>(a.o.dist, i, dist);
     putc<OutT, ALLCOLS>(a.o.mag[SS_BAND_G], i, mag_g);
-#endif
     putc<OutT, ALLCOLS>(a.o.mag[SS_BAND_R], i, mag_r);
     if (HIST && !(SS_WHATIF & 4)) {
       const int b0 = __double2loint(row.thr);                        // host-binned phi1
@@ -972,12 +849,8 @@ k_fused(const __grid_constant__ KArgs a) {
 #else
     rotate_star(p, row.sinx, row.cosx, phi2, wx, wy, wz, lon, ra, dec);
 #endif
-#if SS_VEC_STORES
-    put2<OutT>(a.o.ra, a.o.dec, i, ra, dec, full);
-#else
     putc<OutT, ALLCOLS>(a.o.ra, i, ra);
     putc<OutT, ALLCOLS>(a.o.dec, i, dec);
-#endif
 
     // ------------------------------------------------ observe (observed.py:146-291)
     ss::HpLoc L;
@@ -1011,50 +884,28 @@ k_fused(const __grid_constant__ KArgs a) {
       if (want_cnt) atomicAdd(&s_cnt[SS_CNT_BADCOORD], 1u);
       if (a.o.pix) a.o.pix[i] = -1;
     }
-#if SS_PREP_POS == 2
     if (i + stride < n) prepare(i + stride);                       // n <= 2^31: no wrap-around
     // (the gathered record stays whole until here: see the row loads above)
     asm volatile("" ::"d"(ebv), "d"(ml_g), "d"(ml_r), "d"(map_pad));
-#endif
-#if SS_OBS_EARLY
     const double z_r = (double)zf_r, z_g = (double)zf_g;
-#else
-    const uint4 wo = ss::philox_block_c<SS_DRAW_BLOCK_OBS>(a.offset + i, a.keys);
-    double z_r, z_g;
-    ss::bm32(wo.x, wo.y, z_r, z_g);
-#endif
     ss::ObsOut o;
 #if SS_WHATIF & 8
     o.mobs[0] = mag_g + ebv; o.mobs[1] = mag_r + ml_g; o.err[0] = ml_r; o.err[1] = z_r + z_g;
     o.observed = wo.z > wo.w; o.perfect = false; o.unseen = false; o.bad[0] = o.bad[1] = false;
-#elif SS_QREP
-    ss::observe_star<MATH, 2>(p, tab, share, true, true, mag_g, mag_r, ebv, ml_g, ml_r, z_g, z_r,
-                              ss::u32(wo.z), ss::u32(wo.w), o, &qrep);
 #else
-    ss::observe_star<MATH, SS_QCURVE != 0>(p, tab, share, true, true, mag_g, mag_r, ebv, ml_g, ml_r, z_g,
-                                 z_r, ss::u32(wo.z), ss::u32(wo.w), o);
+    ss::observe_star<MATH, true>(p, tab, share, true, true, mag_g, mag_r, ebv, ml_g, ml_r, z_g, z_r,
+                                 ss::u32(wo.z), ss::u32(wo.w), o);
 #endif
-#if SS_PREP_POS == 1
-    if (i + stride < n) prepare(i + stride);
-#endif
-#if SS_VEC_STORES
-    put2<OutT>(a.o.mag_obs[SS_BAND_G], a.o.magerr[SS_BAND_G], i, o.mobs[SS_BAND_G], o.err[SS_BAND_G], full);
-    put2<OutT>(a.o.mag_obs[SS_BAND_R], a.o.magerr[SS_BAND_R], i, o.mobs[SS_BAND_R], o.err[SS_BAND_R], full);
-#else
     putc<OutT, ALLCOLS>(a.o.mag_obs[SS_BAND_G], i, o.mobs[SS_BAND_G]);
     putc<OutT, ALLCOLS>(a.o.magerr[SS_BAND_G], i, o.err[SS_BAND_G]);
     putc<OutT, ALLCOLS>(a.o.mag_obs[SS_BAND_R], i, o.mobs[SS_BAND_R]);
     putc<OutT, ALLCOLS>(a.o.magerr[SS_BAND_R], i, o.err[SS_BAND_R]);
-#endif
     if (ALLCOLS || a.o.flag_observed) a.o.flag_observed[i] = o.observed ? 1 : 0;
     if (a.o.flag_perfect) a.o.flag_perfect[i] = o.perfect ? 1 : 0;
     c_unseen_badg += (o.unseen ? 1u : 0u) + (o.bad[SS_BAND_G] ? 0x10000u : 0u);
     c_badr_obs += (o.bad[SS_BAND_R] ? 1u : 0u) + (o.observed ? 0x10000u : 0u);
     c_perfect += o.perfect ? 1u : 0u;
 
-#if SS_PREP_POS == 0
-    if (i + stride < n) prepare(i + stride);
-#endif
   }
 
   if (want_cnt) {
@@ -1300,9 +1151,8 @@ bool fused_eligible(const KArgs& a, int smem) {
 }
 
 // dynamic shared memory of k_fused: the hot blob, three 16-byte staging slots per thread (kFusedStage)
-// ... then the bank-group-private copies of the curve records
 int fused_smem(const KArgs& a, int blob_smem) {
-  return blob_smem + kFusedStage + (SS_QREP ? 16 * qrep_layout(a.p).chunks : 0);
+  return blob_smem + kFusedStage;
 }
 
 template <typename OutT, int MATH, bool HIST>
@@ -1545,13 +1395,6 @@ int ss_run(uint32_t stages, const SSParams* p, const SSTables* t, const SSMaps* 
   for (int h = 0; h < SS_N_HIST; ++h) {
     a.hist_lo[h] = (float)p->hist_lo[h];
     a.hist_inv[h] = (float)p->hist_inv_width[h];
-  }
-  {
-    const void* cols[11] = {out->phi1, out->phi2, out->dist, out->mag[0], out->mag[1], out->ra, out->dec,
-                            out->mag_obs[0], out->mag_obs[1], out->magerr[0], out->magerr[1]};
-    uintptr_t bits = 0;
-    for (const void* c : cols) bits |= (uintptr_t)c;
-    a.vec_ok = (bits & 15) == 0;
   }
   for (int b = p->grid_wlut_n; b > 1; b >>= 1) a.grid_wshift++;    // log2 buckets ...
   for (int b = p->iso_wlut_n; b > 1; b >>= 1) a.iso_wshift++;
