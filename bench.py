@@ -416,8 +416,13 @@ def run_gpu(args):
         barrier()
         if r == rank:
             alone_s = min(copy_columns() for _ in range(2))
-    barrier()
-    together_s = ssd.max_over_ranks(min(copy_columns() for _ in range(2)), device)
+    # all ranks at once: every round starts at a barrier and counts as its slowest rank (a
+    # rank's own best time would credit it with the bandwidth the finished ranks left free)
+    together_s = None
+    for _ in range(3):
+        barrier()
+        round_s = ssd.max_over_ranks(copy_columns(), device)
+        together_s = round_s if together_s is None else min(together_s, round_s)
     barrier()
     alone_gbs = n_e2e * bps / alone_s / 1e9
     alone_min_gbs = -ssd.max_over_ranks(-alone_gbs, device)
