@@ -268,7 +268,8 @@ def wholesky_config():
                 isochrone=dict(name="synthetic"))
 
 
-def build_engine(device, nside, survey=None, math="f64", fused=1, workload="pal5", packed="auto"):
+def build_engine(device, nside, survey=None, math="f64", fused=1, workload="pal5", packed="auto",
+                 normals="f32"):
     from helpers import stream_config
     from stream_sim_b200.engine import StarEngine
     from stream_sim_b200.frames import GreatCircleFrame
@@ -279,7 +280,8 @@ def build_engine(device, nside, survey=None, math="f64", fused=1, workload="pal5
     cfg = wholesky_config() if workload == "wholesky" else stream_config("pal5")
     eng = StarEngine(stream=StreamModel(cfg), survey=survey,
                      frame=GreatCircleFrame.from_endpoints(*NOTEBOOK_ENDPOINTS), device=device,
-                     nside=nside, hist=True, math=math, fused_kernel=bool(fused), packed_maps=packed)
+                     nside=nside, hist=True, math=math, fused_kernel=bool(fused), packed_maps=packed,
+                     normals=normals)
     return eng, survey
 
 
@@ -297,7 +299,7 @@ def run_gpu(args):
     prev_affinity = ssd.bind_host_to_gpu(local)
     packed = "auto" if args.packed_maps else False
     eng, survey = build_engine(device, NSIDE, math=args.math, fused=args.fused,
-                               workload=args.workload, packed=packed)
+                               workload=args.workload, packed=packed, normals=args.normals)
     n = args.stars
     dtype = args.dtype
     out = eng.allocate(n, COLUMNS, dtype)
@@ -450,6 +452,8 @@ def run_gpu(args):
                    "maps": "packed (ebv, maglim_g, maglim_r) records, 32 B per pixel" if bool(eng_packed)
                    else "three separate float64 maps",
                    "rng": "philox4x32-10 (device)", "seed": args.seed,
+                   "normals": "fp32 Box-Muller (MUFU), like curand_normal" if args.normals == "f32"
+                   else "double-precision Box-Muller",
                    "math": args.math, "math_note": MATH_NOTE[args.math],
                    "l2": "no per-star inputs; outputs (%.1f GB/step) exceed L2 and are "
                          "rewritten every step; map/table gathers are L2-resident by design"
@@ -613,6 +617,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--math", choices=("f64", "fast"), default="f64",
                     help="arithmetic of the main leg (see MATH_NOTE)")
+    ap.add_argument("--normals", choices=("f32", "f64"), default="f32",
+                    help="f64: the stars' normal draws from a double-precision Box-Muller "
+                         "(SSParams.normals_f64); the default is the fp32 one, like cuRAND's")
     ap.add_argument("--no-other-math", action="store_true",
                     help="skip the supplementary leg that times the other arithmetic mode")
     ap.add_argument("--census", type=int, default=0,

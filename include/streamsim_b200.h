@@ -91,6 +91,7 @@ extern "C" {
  * key = (seed_lo, seed_hi), output words (w0,w1,w2,w3).  Two blocks per star:
  *   U32(a)   = a * 2^-32                       (uniform in [0,1), exact in double)
  *   BM32(a,b): fp32 Box-Muller, radius sqrt(-2 ln y), y = (~a + 0.5)/2^32, angle 2*pi*b/2^32
+ *   BM64(a,b): the same in double (SSParams.normals_f64): angle = pi * (int32)b / 2^31
  *   block 0 (POS): u_phi1 = U32(w0), u_mass = U32(w1),
  *                  (z_phi2, z_dist) = BM32(w2,w3)   [Uniform samplers: U32(w2), U32(w3)]
  *   block 1 (OBS): (z_r, z_g) = BM32(w0,w1) flux noise,
@@ -223,7 +224,10 @@ typedef struct SSParams {
                                k_fused; 0: always the generic k_stars (tests compare the two) */
   int32_t grid_wlut_n;      /* buckets of SSTables.grid_wlut (power of two; 0 = absent)  */
   int32_t iso_wlut_n;       /* buckets of SSTables.iso_wlut  (power of two; 0 = absent)  */
-  int32_t pad2_;
+  int32_t normals_f64;      /* 0 (default): the four normal draws of a star come from an fp32
+                               Box-Muller on the MUFU units (BM32 below); 1: the same two words
+                               per pair through a double-precision Box-Muller (BM64) -- the star
+                               kernels only; costs 12.5 % */
 } SSParams;
 
 typedef struct SSTables {

@@ -95,22 +95,33 @@ def bm32(wa, wb):
             (r * np.sin(np.pi * ang).astype(f)).astype(np.float64))
 
 
-def device_draws(seed, start, n):
+def bm64(wa, wb):
+    """The device's double-precision Box-Muller (SSParams.normals_f64, csrc ``bm64``): the
+    same two words, y = (~wa + 0.5) / 2^32, radius sqrt(-2 ln y), angle pi * int32(wb) / 2^31.
+    Agrees with the kernel to a few ulp (its own log10 / sqrt, CUDA's sincospi)."""
+    y = ((~wa).astype(np.float64) + 0.5) * (1.0 / 4294967296.0)
+    r = np.sqrt(-2.0 * np.log(y))
+    ang = np.pi * (wb.astype(np.int32).astype(np.float64) * 4.656612873077393e-10)
+    return r * np.cos(ang), r * np.sin(ang)
+
+
+def device_draws(seed, start, n, normals="f32"):
     """All per-star draws the kernel derives for stars [start, start+n): two Philox blocks
     per star, layout of include/streamsim_b200.h (SS_DRAW_BLOCK_POS / _OBS).
 
     Returns the dict accepted by :func:`generate` / :func:`observe`.  The uniforms
     (u_phi1, u_mass, u_phi2, u_dist, u_det, u_det2; one 32-bit word each) are exactly the
     device's; the normals (z_phi2, z_dist, z_r, z_g) are the float32 emulation of
-    :func:`bm32`.
+    :func:`bm32` (``normals="f64"``: of :func:`bm64`).
     """
+    bm = bm64 if normals == "f64" else bm32
     idx = np.arange(start, start + n, dtype=np.uint64)
     w = philox_block(seed, idx, 0)
     u_phi1, u_mass = _u32(w[0]), _u32(w[1])
-    z_phi2, z_dist = bm32(w[2], w[3])
+    z_phi2, z_dist = bm(w[2], w[3])
     u_phi2, u_dist = _u32(w[2]), _u32(w[3])
     w = philox_block(seed, idx, 1)
-    z_r, z_g = bm32(w[0], w[1])
+    z_r, z_g = bm(w[0], w[1])
     u_det, u_det2 = _u32(w[2]), _u32(w[3])
     return dict(u_phi1=u_phi1, u_mass=u_mass, u_phi2=u_phi2, u_dist=u_dist,
                 z_phi2=z_phi2, z_dist=z_dist, z_r=z_r, z_g=z_g,

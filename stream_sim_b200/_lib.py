@@ -66,7 +66,7 @@ class SSParams(C.Structure):
         ("hist_enable", _i32), ("grid_lut_n", _i32),
         ("hist_lo", _f64 * N_HIST), ("hist_inv_width", _f64 * N_HIST),
         ("math_mode", _i32), ("iso_lut_n", _i32), ("grid_nthr", _i32), ("fused_kernel", _i32),
-        ("grid_wlut_n", _i32), ("iso_wlut_n", _i32), ("pad2_", _i32)]
+        ("grid_wlut_n", _i32), ("iso_wlut_n", _i32), ("normals_f64", _i32)]
 
 
 class SSTables(C.Structure):

@@ -406,6 +406,22 @@ __device__ __forceinline__ void sincos_small(double b, double& s, double& c) {
   }
 }
 
+// Box-Muller in double from the same two words (SSParams.normals_f64): y = (~wa + 0.5) / 2^32,
+// radius sqrt(-2 ln y), angle pi * (int32)wb / 2^31 -- bm32f's formulas, every step in double
+__device__ __forceinline__ void bm64(uint32_t wa, uint32_t wb, double& z0, double& z1) {
+  const double y = (word_to_double(~wa) + 0.5) * (1.0 / 4294967296.0);
+  const double r = sqrt_nb(-4.605170185988092 * log10_nb(y));      // -2 ln 10 * log10(y)
+  double s, c;
+  sincospi((double)(int)wb * 4.656612873077393e-10, &s, &c);
+  z0 = r * c;
+  z1 = r * s;
+}
+
+__device__ __forceinline__ void normal_pair(bool f64, uint32_t wa, uint32_t wb, double& z0, double& z1) {
+  if (f64) bm64(wa, wb, z0, z1);
+  else bm32(wa, wb, z0, z1);
+}
+
 // ---------------------------------------------------------------- table search
 // last j in [lo, hi) with xp[j] <= x.  Requires xp[lo] <= x and (hi == n or xp[hi] > x).
 __device__ __forceinline__ int search_le(const double* __restrict__ xp, int lo, int hi, double x) {

@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
       double u_phi1 = d_u_phi1 ? d_u_phi1[i] : ss::u32(w.x);
       const double u_mass = d_u_mass ? d_u_mass[i] : ss::u32(w.y);
       double z0 = 0, z1 = 0;
-      if (!all_given && (z_track || (has_dist && z_dist))) ss::bm32(w.z, w.w, z0, z1);
+      if (!all_given && (z_track || (has_dist && z_dist))) ss::normal_pair(p.normals_f64 != 0, w.z, w.w, z0, z1);
       const double n_phi2 = d_n_phi2 ? d_n_phi2[i] : (z_track ? z0 : ss::u32(w.z));
       const double n_dist = d_n_dist ? d_n_dist[i] : (z_dist ? z1 : ss::u32(w.w));
 
@@ -545,7 +545,7 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
         if (!d_u_phi1) {
           double zz;
           const uint4 wz4 = ss::philox_block(gi, SS_DRAW_BLOCK_DENSITY_Z, a.keys);
-          ss::bm32(wz4.x, wz4.y, u_phi1, zz);
+          ss::normal_pair(p.normals_f64 != 0, wz4.x, wz4.y, u_phi1, zz);
         }
         phi1 = __dadd_rn(__dmul_rn(u_phi1, p.density_hi), p.density_lo);
       } else {
@@ -648,7 +648,7 @@ __global__ void __launch_bounds__(SS_BLOCK, 1) k_stars(const __grid_constant__ K
       double z_r = 0, z_g = 0;
       if (!all_given) {
         w = ss::philox_block(gi, SS_DRAW_BLOCK_OBS, a.keys);
-        ss::bm32(w.x, w.y, z_r, z_g);
+        ss::normal_pair(p.normals_f64 != 0, w.x, w.y, z_r, z_g);
       }
       if (d_z_g) z_g = d_z_g[i];
       if (d_z_r) z_r = d_z_r[i];
@@ -756,6 +756,7 @@ k_fused(const __grid_constant__ KArgs a) {
   const uint32_t stride = gridDim.x * blockDim.x;
   const bool z_track = p.track_sampler == SS_SAMPLER_GAUSSIAN;
   const bool z_dist = p.dist_sampler == SS_SAMPLER_GAUSSIAN;
+  const bool nf64 = p.normals_f64 != 0;
 
   const uint4* __restrict__ const glut = reinterpret_cast<const uint4*>(a.t.grid_wlut);
   const uint4* __restrict__ const ilut = reinterpret_cast<const uint4*>(a.t.iso_wlut);
@@ -808,10 +809,21 @@ k_fused(const __grid_constant__ KArgs a) {
     const Double4 ri = ldg256(a.t.iso_rows + 4 * si);
 #endif
     const uint4 wo = ss::philox_block_c<SS_DRAW_BLOCK_OBS>(a.offset + i, a.keys);
-    float zf_r, zf_g;
-    ss::bm32f(wo.x, wo.y, zf_r, zf_g);
-    float zf0 = 0.0f, zf1 = 0.0f;
-    if (z_track || z_dist) ss::bm32f(wp.z, wp.w, zf0, zf1);
+    // the flux-noise normals travel to the observe stage as two fp32 values -- or, with
+    // double-precision normals, as the two words they are made of there
+    uint32_t c_r = wo.x, c_g = wo.y;
+    double nz0 = 0.0, nz1 = 0.0;
+    if (nf64) {
+      if (z_track || z_dist) ss::bm64(wp.z, wp.w, nz0, nz1);
+    } else {
+      float zf_r, zf_g, zf0 = 0.0f, zf1 = 0.0f;
+      ss::bm32f(wo.x, wo.y, zf_r, zf_g);
+      if (z_track || z_dist) ss::bm32f(wp.z, wp.w, zf0, zf1);
+      c_r = __float_as_uint(zf_r);
+      c_g = __float_as_uint(zf_g);
+      nz0 = (double)zf0;
+      nz1 = (double)zf1;
+    }
     asm volatile("" ::"d"(g0.a), "d"(g0.b), "d"(g0.c), "d"(g0.d), "d"(g1.a), "d"(g1.b), "d"(g1.c),
                  "d"(g1.d), "d"(ri.a), "d"(ri.b), "d"(ri.c), "d"(ri.d));
     GridRow row;
@@ -819,8 +831,8 @@ k_fused(const __grid_constant__ KArgs a) {
     row.dc = g1.a; row.ds = g1.b; row.sinx = g1.c; row.cosx = g1.d;
     const double m1 = fma(ri.b, u_mass, ri.a), m2 = fma(ri.d, u_mass, ri.c);
     // the two track draws: normals (fp32 Box-Muller) or uniforms, per the samplers
-    const double n_phi2 = z_track ? (double)zf0 : ss::u32(wp.z);
-    const double n_dist = z_dist ? (double)zf1 : ss::u32(wp.w);
+    const double n_phi2 = z_track ? nz0 : ss::u32(wp.z);
+    const double n_dist = z_dist ? nz1 : ss::u32(wp.w);
     unsigned c_dom = 0;
     const double phi2 = track_draw(row.c, row.s, p.track_sampler, n_phi2, c_dom);
     const double dist = track_draw(row.dc, row.ds, p.dist_sampler, n_dist, c_dom);
@@ -887,7 +899,8 @@ k_fused(const __grid_constant__ KArgs a) {
     if (i + stride < n) prepare(i + stride);                       // n <= 2^31: no wrap-around
     // (the gathered record stays whole until here: see the row loads above)
     asm volatile("" ::"d"(ebv), "d"(ml_g), "d"(ml_r), "d"(map_pad));
-    const double z_r = (double)zf_r, z_g = (double)zf_g;
+    double z_r = (double)__uint_as_float(c_r), z_g = (double)__uint_as_float(c_g);
+    if (nf64) ss::bm64(c_r, c_g, z_r, z_g);
     ss::ObsOut o;
 #if SS_WHATIF & 8
     o.mobs[0] = mag_g + ebv; o.mobs[1] = mag_r + ml_g; o.err[0] = ml_r; o.err[1] = z_r + z_g;

@@ -460,7 +460,7 @@ class StarEngine:
                  nside=4096, dust_correction=True, perfect_galstarsep=False,
                  detection_mag_cut=("g",), nest=False, hist=None, cdf_steps=1e5,
                  grid_table=True, math="f64", iso_direct=True, fused_kernel=True,
-                 packed_maps="auto"):
+                 packed_maps="auto", normals="f32"):
         torch = _torch()
         self.lib = _lib.load()
         self.device = require_device(device)
@@ -482,6 +482,9 @@ class StarEngine:
             raise ValueError("math must be 'f64' or 'fast'")
         self.params.math_mode = _lib.MATH_FAST if math == "fast" else _lib.MATH_F64
         self.params.fused_kernel = int(bool(fused_kernel))
+        if normals not in ("f32", "f64"):
+            raise ValueError("normals must be 'f32' (fp32 Box-Muller, the default) or 'f64'")
+        self.params.normals_f64 = int(normals == "f64")
         self._packed_maps = packed_maps
         self._describe_hist(hist)          # before the stream: the phi1 grid rows carry their bin
         if survey is not None:

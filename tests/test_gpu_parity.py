@@ -228,6 +228,36 @@ def test_device_normals_are_standard_normal(torch_cuda):
         assert stats.kstest(d[k], "uniform").pvalue > 1e-3, k
 
 
+def test_double_precision_normals_switch(torch_cuda):
+    """StarEngine(normals="f64") -- the four normal draws of a star from a double-precision
+    Box-Muller of the same Philox words (SSParams.normals_f64): the exported draws equal the
+    oracle's NumPy emulation to a few ulp, production and generic kernel agree byte for byte,
+    the oracle fed with those draws reproduces the run, and the uniforms are untouched."""
+    from scipy import stats
+    n, seed = 1 << 18, 31
+    eng, _ = _fused_engine("toy1", normals="f64")        # Gaussian track: z_phi2 is a normal
+    out = eng.generate_observe(n, seed=seed, pix=True, export_draws=True)   # generic kernel
+    fused = eng.generate_observe(n, seed=seed, pix=True)                      # production kernel
+    for k, v in fused.items():
+        assert torch_cuda.equal(v.view(torch_cuda.uint8), out[k].view(torch_cuda.uint8)), k
+    d = eng.exported_draws(out)
+    want = oracle.device_draws(seed, 0, n, normals="f64")
+    for k in ("z_phi2", "z_r", "z_g"):
+        assert np.abs(d[k] - want[k]).max() < 1e-13, k
+        assert stats.kstest(d[k], "norm").pvalue > 1e-3, k
+    f32 = oracle.device_draws(seed, 0, n)
+    assert np.abs(want["z_r"] - f32["z_r"]).max() > 1e-9          # it is a different draw ...
+    assert np.abs(want["z_r"] - f32["z_r"]).max() < 1e-2          # ... of the same pair of words
+    for k in ("u_phi1", "u_mass", "u_det", "u_det2"):
+        assert np.array_equal(d[k], want[k]), k
+    ref = _oracle_fused("toy1", d)
+    got = {k: v.cpu().numpy() for k, v in out.items() if k != "draws"}
+    assert np.array_equal(got["pix"], ref["pix"])
+    assert np.array_equal(got["flag_observed"].astype(bool), ref["flag_observed"])
+    for k in ("phi2", "dist", "mag_g_obs", "mag_r_obs", "magerr_r"):
+        assert np.allclose(got[k], ref[k], rtol=1e-9, atol=1e-9, equal_nan=True), k
+
+
 def test_shard_invariance_and_offsets(torch_cuda):
     """Any split of the global index range gives identical per-star bytes."""
     n = 100003
