@@ -269,7 +269,7 @@ def wholesky_config():
 
 
 def build_engine(device, nside, survey=None, math="f64", fused=1, workload="pal5", packed="auto",
-                 normals="f32"):
+                 normals="f32", map_dtype="f64"):
     from helpers import stream_config
     from stream_sim_b200.engine import StarEngine
     from stream_sim_b200.frames import GreatCircleFrame
@@ -281,7 +281,7 @@ def build_engine(device, nside, survey=None, math="f64", fused=1, workload="pal5
     eng = StarEngine(stream=StreamModel(cfg), survey=survey,
                      frame=GreatCircleFrame.from_endpoints(*NOTEBOOK_ENDPOINTS), device=device,
                      nside=nside, hist=True, math=math, fused_kernel=bool(fused), packed_maps=packed,
-                     normals=normals)
+                     normals=normals, map_dtype=map_dtype)
     return eng, survey
 
 
@@ -299,7 +299,8 @@ def run_gpu(args):
     prev_affinity = ssd.bind_host_to_gpu(local)
     packed = "auto" if args.packed_maps else False
     eng, survey = build_engine(device, NSIDE, math=args.math, fused=args.fused,
-                               workload=args.workload, packed=packed, normals=args.normals)
+                               workload=args.workload, packed=packed, normals=args.normals,
+                               map_dtype=args.maps)
     n = args.stars
     dtype = args.dtype
     out = eng.allocate(n, COLUMNS, dtype)
@@ -449,7 +450,9 @@ def run_gpu(args):
                    "nside": NSIDE,
                    "stream": "config/pal5_config.yaml + synthetic isochrone" if args.workload == "pal5"
                    else "stress variant: flat density over phi1 in [-180,180], 40-deg Gaussian width",
-                   "maps": "packed (ebv, maglim_g, maglim_r) records, 32 B per pixel" if bool(eng_packed)
+                   "maps": "NON-PARITY OPTION: survey maps rounded to fp32, packed records, 16 B per pixel"
+                   if args.maps == "f32" else
+                   "packed (ebv, maglim_g, maglim_r) records, 32 B per pixel" if bool(eng_packed)
                    else "three separate float64 maps",
                    "rng": "philox4x32-10 (device)", "seed": args.seed,
                    "normals": "fp32 Box-Muller (MUFU), like curand_normal" if args.normals == "f32"
@@ -617,6 +620,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--math", choices=("f64", "fast"), default="f64",
                     help="arithmetic of the main leg (see MATH_NOTE)")
+    ap.add_argument("--maps", choices=("f64", "f32"), default="f64",
+                    help="f32: survey maps rounded to fp32 and gathered as 16-byte records -- a "
+                         "labelled non-parity option (the reference's maps are float64)")
     ap.add_argument("--normals", choices=("f32", "f64"), default="f32",
                     help="f64: the stars' normal draws from a double-precision Box-Muller "
                          "(SSParams.normals_f64); the default is the fp32 one, like cuRAND's")

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SS_ABI_VERSION 14
+#define SS_ABI_VERSION 15
 
 /* error codes */
 #define SS_OK 0
@@ -290,6 +290,11 @@ typedef struct SSMaps {
    * when the three maps share one nside (0 = absent). */
   int32_t nside_packed;
   const double* packed;
+  /* optional, instead of `packed`: the same records in fp32, [12*nside_packed^2][4 floats] --
+   * one 16-byte gather, half the footprint.  NOT the reference's arithmetic: the survey maps
+   * are rounded to fp32 first (the host then also hands the separate maps over rounded, so
+   * that every kernel sees the same values); a labelled option, never the default. */
+  const float* packed32;
 } SSMaps;
 
 typedef struct SSCatalog {   /* per-star inputs of the stages that are not run */

@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 14
+ABI_VERSION = 15
 
 # ---- constants mirrored from the header
 STAGE_GENERATE, STAGE_ROTATE, STAGE_OBSERVE = 1, 2, 4
@@ -78,7 +78,7 @@ class SSTables(C.Structure):
 
 class SSMaps(C.Structure):
     _fields_ = [("ebv", _vp), ("maglim", _vp * 2), ("mask", _vp), ("nside_mask", _i32),
-                ("nside_packed", _i32), ("packed", _vp)]
+                ("nside_packed", _i32), ("packed", _vp), ("packed32", _vp)]
 
 
 class SSCatalog(C.Structure):

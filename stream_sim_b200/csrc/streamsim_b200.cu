@@ -38,6 +38,14 @@
 #define SS_HP32 1
 #endif
 
+// 1: k_fused writes pairs of fp64 columns with 128-bit stores (neighbouring lanes exchange one
+// value each).  A measured build option: STG.E.128 in the SASS, parity subset green, 2 % SLOWER
+// than the scalar stores (profiles/r02_variants_maps_and_stores.json) -- the bytes per L1
+// pass are the same and the exchange costs issue slots.  Off.
+#ifndef SS_VEC_STORES
+#define SS_VEC_STORES 0
+#endif
+
 // what-if builds (development only; results are wrong on purpose): leave one component of
 // k_fused out to measure what it costs.  1 = no map gather, 2 = no column stores, 4 = no
 // histogram / counter updates, 8 = no observe arithmetic, 16 = no rotation, 32 = no row loads,
@@ -78,6 +86,7 @@ struct KArgs {
   // histogram origins / inverse bin widths rounded to fp32
   ss::PhiloxKeys keys;
   float hist_lo[SS_N_HIST], hist_inv[SS_N_HIST];
+  int vec_ok;   // every floating-point column is 16-byte aligned (SS_VEC_STORES)
   int grid_wshift, iso_wshift;   // bucket of a word table = w >> shift
 };
 
@@ -138,6 +147,25 @@ __device__ __forceinline__ void putc(void* col, unsigned long long i, double v) 
 #else
   if (SURE || col) reinterpret_cast<T*>(col)[i] = (T)v;
 #endif
+}
+
+// Two columns, one 16-byte store per lane: neighbouring lanes swap one value each (even lanes
+// end up with column A of both stars, odd lanes with column B), so a warp writes its 2 x 256
+// bytes as 32 STG.E.128 instead of 64 STG.E.64.  `full` = the whole warp is inside the range
+// (warp-uniform); the ragged last warp and fp32 columns take the scalar stores.
+template <typename OutT>
+__device__ __forceinline__ void put2(void* ca, void* cb, unsigned long long i, double va, double vb,
+                                     bool full) {
+  if (sizeof(OutT) == 8 && full && ca && cb) {
+    const bool odd = (threadIdx.x & 1) != 0;
+    const double recv = __shfl_xor_sync(0xffffffffu, odd ? va : vb, 1);
+    const double2 v = odd ? make_double2(recv, vb) : make_double2(va, recv);
+    double* const col = reinterpret_cast<double*>(odd ? cb : ca);
+    *reinterpret_cast<double2*>(col + (i & ~1ULL)) = v;
+  } else {
+    put<OutT>(ca, i, va);
+    put<OutT>(cb, i, vb);
+  }
 }
 
 // centre and spread of a TrackModel at x (reference model.py:517-518)
@@ -838,10 +866,16 @@ k_fused(const __grid_constant__ KArgs a) {
     const double dist = track_draw(row.dc, row.ds, p.dist_sampler, n_dist, c_dom);
     if (c_dom && want_cnt) atomicAdd(&s_cnt[SS_CNT_DOMAIN], c_dom);
     const double mag_g = __dadd_rn(m1, dist), mag_r = __dadd_rn(m2, dist);
+#if SS_VEC_STORES
+    const bool full = a.vec_ok && (i | 31u) < n;                   // warp-uniform
+    put2<OutT>(a.o.phi1, a.o.phi2, i, row.x, phi2, full);
+    put2<OutT>(a.o.dist, a.o.mag[SS_BAND_G], i, dist, mag_g, full);
+#else
     putc<OutT, ALLCOLS>(a.o.phi1, i, row.x);
     putc<OutT, ALLCOLS>(a.o.phi2, i, phi2);
     putc<OutT, ALLCOLS>(a.o.dist, i, dist);
     putc<OutT, ALLCOLS>(a.o.mag[SS_BAND_G], i, mag_g);
+#endif
     putc<OutT, ALLCOLS>(a.o.mag[SS_BAND_R], i, mag_r);
     if (HIST && !(SS_WHATIF & 4)) {
       const int b0 = __double2loint(row.thr);                        // host-binned phi1
@@ -861,8 +895,12 @@ k_fused(const __grid_constant__ KArgs a) {
 #else
     rotate_star(p, row.sinx, row.cosx, phi2, wx, wy, wz, lon, ra, dec);
 #endif
+#if SS_VEC_STORES
+    put2<OutT>(a.o.ra, a.o.dec, i, ra, dec, full);
+#else
     putc<OutT, ALLCOLS>(a.o.ra, i, ra);
     putc<OutT, ALLCOLS>(a.o.dec, i, dec);
+#endif
 
     // ------------------------------------------------ observe (observed.py:146-291)
     ss::HpLoc L;
@@ -879,8 +917,13 @@ k_fused(const __grid_constant__ KArgs a) {
       if (SS_WHATIF & 1) {
         ebv = 0.05 + 1e-9 * (double)(pe & 1023); ml_g = 26.0; ml_r = 25.7;
       } else if (PACKED) {
-        const Double4 r = ldg256(a.m.packed + 4 * pe);
-        ebv = r.a; ml_g = r.b; ml_r = r.c; map_pad = r.d;
+        if (a.m.packed32) {                                          // fp32 records (option)
+          const float4 r = __ldg(reinterpret_cast<const float4*>(a.m.packed32) + pe);
+          ebv = (double)r.x; ml_g = (double)r.y; ml_r = (double)r.z; map_pad = (double)r.w;
+        } else {
+          const Double4 r = ldg256(a.m.packed + 4 * pe);
+          ebv = r.a; ml_g = r.b; ml_r = r.c; map_pad = r.d;
+        }
       } else {
         ebv = __ldg(&a.m.ebv[pe]);
         const long long pg = (p.nside_maglim[SS_BAND_G] == p.nside_ebv)
@@ -909,10 +952,15 @@ k_fused(const __grid_constant__ KArgs a) {
     ss::observe_star<MATH, true>(p, tab, share, true, true, mag_g, mag_r, ebv, ml_g, ml_r, z_g, z_r,
                                  ss::u32(wo.z), ss::u32(wo.w), o);
 #endif
+#if SS_VEC_STORES
+    put2<OutT>(a.o.mag_obs[SS_BAND_G], a.o.magerr[SS_BAND_G], i, o.mobs[SS_BAND_G], o.err[SS_BAND_G], full);
+    put2<OutT>(a.o.mag_obs[SS_BAND_R], a.o.magerr[SS_BAND_R], i, o.mobs[SS_BAND_R], o.err[SS_BAND_R], full);
+#else
     putc<OutT, ALLCOLS>(a.o.mag_obs[SS_BAND_G], i, o.mobs[SS_BAND_G]);
     putc<OutT, ALLCOLS>(a.o.magerr[SS_BAND_G], i, o.err[SS_BAND_G]);
     putc<OutT, ALLCOLS>(a.o.mag_obs[SS_BAND_R], i, o.mobs[SS_BAND_R]);
     putc<OutT, ALLCOLS>(a.o.magerr[SS_BAND_R], i, o.err[SS_BAND_R]);
+#endif
     if (ALLCOLS || a.o.flag_observed) a.o.flag_observed[i] = o.observed ? 1 : 0;
     if (a.o.flag_perfect) a.o.flag_perfect[i] = o.perfect ? 1 : 0;
     c_unseen_badg += (o.unseen ? 1u : 0u) + (o.bad[SS_BAND_G] ? 0x10000u : 0u);
@@ -1171,7 +1219,7 @@ int fused_smem(const KArgs& a, int blob_smem) {
 template <typename OutT, int MATH, bool HIST>
 int launch_fused_p(const KArgs& a, int smem, int grid, cudaStream_t s) {
   const SSParams& p = a.p;
-  const bool packed = a.m.packed && a.m.nside_packed == p.nside_ebv &&
+  const bool packed = (a.m.packed || a.m.packed32) && a.m.nside_packed == p.nside_ebv &&
                       p.nside_maglim[0] == p.nside_ebv && p.nside_maglim[1] == p.nside_ebv;
   const int total = fused_smem(a, smem);
   const SSOut& o = a.o;
@@ -1300,6 +1348,8 @@ int validate(uint32_t st, const SSParams* p, const SSTables* t, const SSMaps* m,
     if (!m->ebv) return fail(SS_EINVAL, "E(B-V) map not loaded%s");
     if (m->packed && ((uintptr_t)m->packed & 31))
       return fail(SS_EINVAL, "SSMaps.packed must be 32-byte aligned%s");
+    if (m->packed32 && ((uintptr_t)m->packed32 & 15))
+      return fail(SS_EINVAL, "SSMaps.packed32 must be 16-byte aligned%s");
     for (int b = 0; b < 2; ++b)
       if (p->band_present[b] && !m->maglim[b]) return fail(SS_EINVAL, "maglim map missing for a requested band%s");
     if (!p->band_present[p->completeness_band & 1])
@@ -1408,6 +1458,13 @@ int ss_run(uint32_t stages, const SSParams* p, const SSTables* t, const SSMaps* 
   for (int h = 0; h < SS_N_HIST; ++h) {
     a.hist_lo[h] = (float)p->hist_lo[h];
     a.hist_inv[h] = (float)p->hist_inv_width[h];
+  }
+  {
+    const void* cols[11] = {out->phi1, out->phi2, out->dist, out->mag[0], out->mag[1], out->ra, out->dec,
+                            out->mag_obs[0], out->mag_obs[1], out->magerr[0], out->magerr[1]};
+    uintptr_t bits = 0;
+    for (const void* c : cols) bits |= (uintptr_t)c;
+    a.vec_ok = (bits & 15) == 0;
   }
   for (int b = p->grid_wlut_n; b > 1; b >>= 1) a.grid_wshift++;    // log2 buckets ...
   for (int b = p->iso_wlut_n; b > 1; b >>= 1) a.iso_wshift++;

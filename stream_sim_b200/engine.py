@@ -460,7 +460,7 @@ class StarEngine:
                  nside=4096, dust_correction=True, perfect_galstarsep=False,
                  detection_mag_cut=("g",), nest=False, hist=None, cdf_steps=1e5,
                  grid_table=True, math="f64", iso_direct=True, fused_kernel=True,
-                 packed_maps="auto", normals="f32"):
+                 packed_maps="auto", normals="f32", map_dtype="f64"):
         torch = _torch()
         self.lib = _lib.load()
         self.device = require_device(device)
@@ -482,6 +482,9 @@ class StarEngine:
             raise ValueError("math must be 'f64' or 'fast'")
         self.params.math_mode = _lib.MATH_FAST if math == "fast" else _lib.MATH_F64
         self.params.fused_kernel = int(bool(fused_kernel))
+        if map_dtype not in ("f64", "f32"):
+            raise ValueError("map_dtype must be 'f64' (the reference's) or 'f32'")
+        self._map_f32 = map_dtype == "f32"
         if normals not in ("f32", "f64"):
             raise ValueError("normals must be 'f32' (fp32 Box-Muller, the default) or 'f64'")
         self.params.normals_f64 = int(normals == "f64")
@@ -739,6 +742,8 @@ class StarEngine:
                 t = arr.to(device=self.device, dtype=torch.float64).contiguous()
             else:
                 t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64)).to(self.device)
+            if self._map_f32:                  # map_dtype="f32": every kernel sees the rounded values
+                t = t.to(torch.float32).to(torch.float64)
             self._keep.append(t)
             return t
 
@@ -795,6 +800,14 @@ class StarEngine:
         if not want or not same:
             return
         npix = 12 * p.nside_ebv ** 2
+        if self._map_f32:
+            packed = torch.zeros((npix, 4), dtype=torch.float32, device=self.device)
+            for col, key in enumerate(("ebv", "g", "r")):
+                packed[:, col] = self._map_tensors[key].to(torch.float32)
+            self.packed_maps = packed
+            self.maps.packed32 = packed.data_ptr()
+            self.maps.nside_packed = p.nside_ebv
+            return
         if want == "auto":
             free, _ = torch.cuda.mem_get_info(self.device)
             if 32 * npix > 0.25 * free:

@@ -258,6 +258,39 @@ def test_double_precision_normals_switch(torch_cuda):
         assert np.allclose(got[k], ref[k], rtol=1e-9, atol=1e-9, equal_nan=True), k
 
 
+def test_fp32_map_option(torch_cuda):
+    """StarEngine(map_dtype="f32") -- a labelled non-parity option: the survey maps rounded to
+    fp32 and gathered as 16-byte packed records.  What it computes is the reference's chain on
+    the ROUNDED maps: production and generic kernel agree byte for byte, the oracle fed with the
+    rounded maps reproduces pix, both flags and the columns, and against the float64 maps only
+    a handful of flags move (stars within ~1e-7 mag of a decision)."""
+    n, seed = 1 << 19, 17
+    nsides = (512, 512)                                   # one nside: the packed form applies
+    eng, _ = _fused_engine("pal5", nsides=nsides, map_dtype="f32")
+    assert eng.maps.packed32 and not eng.maps.packed
+    out = eng.generate_observe(n, seed=seed, pix=True, export_draws=True)     # generic kernel
+    fused = eng.generate_observe(n, seed=seed, pix=True)                        # production kernel
+    for k, v in fused.items():
+        assert torch_cuda.equal(v.view(torch_cuda.uint8), out[k].view(torch_cuda.uint8)), k
+    from stream_sim_b200.synthetic import NOTEBOOK_ENDPOINTS, isochrone_table
+    R = oracle.frame_from_endpoints(*NOTEBOOK_ENDPOINTS[0], *NOTEBOOK_ENDPOINTS[1])
+    sv = oracle_survey("r", nside_maglim=nsides[0], nside_ebv=nsides[1])
+    rnd = lambda m: np.asarray(m, dtype=np.float64).astype(np.float32).astype(np.float64)
+    sv32 = dict(sv, ebv_map=rnd(sv["ebv_map"]), maglim_maps={b: rnd(m) for b, m in sv["maglim_maps"].items()})
+    d = eng.exported_draws(out)
+    got = {k: v.cpu().numpy() for k, v in out.items() if k != "draws"}
+    ref = oracle.generate_observe(stream_config("pal5"), isochrone_table(), R, sv32, d)
+    assert np.array_equal(got["pix"], ref["pix"])
+    assert np.array_equal(got["flag_observed"].astype(bool), ref["flag_observed"])
+    for k in ("mag_g_obs", "mag_r_obs", "magerr_g", "magerr_r"):
+        assert np.allclose(got[k], ref[k], rtol=1e-9, atol=1e-9, equal_nan=True), k
+    ref64 = oracle.generate_observe(stream_config("pal5"), isochrone_table(), R, sv, d)
+    moved = np.count_nonzero(got["flag_observed"].astype(bool) != ref64["flag_observed"])
+    assert moved <= 5, moved
+    ok = np.isfinite(ref64["magerr_r"]) & np.isfinite(got["magerr_r"])
+    assert np.abs(got["magerr_r"][ok] / ref64["magerr_r"][ok] - 1).max() < 1e-5
+
+
 def test_shard_invariance_and_offsets(torch_cuda):
     """Any split of the global index range gives identical per-star bytes."""
     n = 100003
