@@ -39,12 +39,14 @@
 #endif
 
 // 1: k_fused writes pairs of fp64 columns with 128-bit stores (neighbouring lanes exchange one
-// value each).  A measured build option: STG.E.128 in the SASS, parity subset green, 2 % SLOWER
-// than the scalar stores (profiles/r02_variants_maps_and_stores.json) -- the bytes per L1
-// pass are the same and the exchange costs issue slots.  Off.
+// value each).  A measured build option: STG.E.128 in the SASS (profiles/r02_vecstores_sass_
+// excerpt.txt), parity subset green, 2 % slower than the scalar stores in the round-2 interim
+// kernel and 8 % in the final one (profiles/r02_build_variants.json) -- the bytes per L1 pass
+// are the same and the exchange costs issue slots.  Off.
 #ifndef SS_VEC_STORES
 #define SS_VEC_STORES 0
 #endif
+// (cache hints on the column stores -- st.global.cs / .wt / .cg -- change nothing: measured)
 
 // what-if builds (development only; results are wrong on purpose): leave one component of
 // k_fused out to measure what it costs.  1 = no map gather, 2 = no column stores, 4 = no
