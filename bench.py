@@ -431,6 +431,29 @@ def run_gpu(args):
     alone_min_gbs = -ssd.max_over_ranks(-alone_gbs, device)
     ceiling_gbs = world * n_e2e * bps / together_s / 1e9
 
+    # a separate, labelled leg: the same call with fp32 output columns (45 B per star instead of
+    # 89) -- NOT the headline, which stays on the reference's float64 columns
+    e2e_f32 = None
+    if dtype == "f64" and not args.no_e2e:
+        del host, ws                      # one set of pinned buffers at a time
+        host32 = eng.allocate_host(n_e2e, COLUMNS, "f32")
+        ws32 = eng.host_workspace(chunk, "f32")
+
+        def e2e32_step(k):
+            eng.generate_observe_host(n_e2e, host32, ws32, chunk, seed=args.seed,
+                                      offset=(k * world + rank) * n_e2e, dtype="f32")
+        e2e32_step(0)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            e2e32_step(1 + k)
+        barrier()
+        s32 = ssd.max_over_ranks(time.perf_counter() - t0, device)
+        v32 = world * n_e2e * e2e_steps / s32
+        e2e_f32 = {"value": v32, "unit": "stars/s", "gbs": v32 * 45 / 1e9,
+                   "note": "same call, fp32 output columns (45 B/star): a labelled extra, not the headline"}
+        del host32, ws32
+
     if world > 1:
         dist.destroy_process_group()
     if rank != 0:
@@ -489,6 +512,7 @@ def run_gpu(args):
                 "ceiling_note": "plain cudaMemcpyAsync of the same 12 columns into the same pinned "
                                 "buffers: pcie_gbs = slowest rank copying alone, copy_ceiling_gbs = "
                                 "all ranks copying at once (whole job)",
+                "fp32_columns": e2e_f32,
                 "host_numa_bound": prev_affinity is not None},
         "gpu_launches": args.steps,
         "clocks": clocks,
