@@ -257,15 +257,10 @@ MATH_NOTE = {
 
 
 def wholesky_config():
-    """Stress variant: stars spread over the whole sky -- flat density along
-    phi1 in [-180, 180], a 40-degree-wide Gaussian across -- so that every map gather goes to
-    a different part of the 200-million-pixel maps and misses L2."""
-    return dict(density=dict(type="Interpolation", xvals=[-180.0, 180.0], yvals=[1.0, 1.0]),
-                track=dict(center=dict(type="Constant", value=0.0),
-                           spread=dict(type="Constant", value=40.0), sampler="Gaussian"),
-                distance_modulus=dict(center=dict(type="Line", slope=0.0, intercept=16.5),
-                                      spread=dict(type="Constant", value=0.3), sampler="Gaussian"),
-                isochrone=dict(name="synthetic"))
+    """Stress variant: stars spread over the whole sky, so that every map
+    gather goes to a different part of the 200-million-pixel maps and misses L2."""
+    from helpers import stream_config
+    return stream_config("wholesky")
 
 
 def build_engine(device, nside, survey=None, math="f64", fused=1, workload="pal5", packed="auto",

@@ -48,6 +48,15 @@ def stream_config(name):
     ``atlas_spline`` / ``phoenix_spline``: the Patrick et al. (2022) spline streams with
     their distance-modulus splines (the configs of the golden generate fixtures)."""
     from stream_sim_b200.utils import parse_config
+    if name == "wholesky":
+        # stress variant (SURVEY section 8d): stars over the whole sky -- flat density along phi1
+        # in [-180, 180], a wide Gaussian across: both polar caps, every base face, the poles
+        return dict(density=dict(type="Interpolation", xvals=[-180.0, 180.0], yvals=[1.0, 1.0]),
+                    track=dict(center=dict(type="Constant", value=0.0),
+                               spread=dict(type="Constant", value=40.0), sampler="Gaussian"),
+                    distance_modulus=dict(center=dict(type="Line", slope=0.0, intercept=16.5),
+                                          spread=dict(type="Constant", value=0.3), sampler="Gaussian"),
+                    isochrone=dict(name="synthetic"))
     if name in ("atlas_spline", "phoenix_spline"):
         f = "./data/patrick_2022_splines.csv"
         sn = name.split("_")[0]

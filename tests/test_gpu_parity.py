@@ -258,6 +258,31 @@ def test_double_precision_normals_switch(torch_cuda):
         assert np.allclose(got[k], ref[k], rtol=1e-9, atol=1e-9, equal_nan=True), k
 
 
+def test_whole_sky_matches_oracle(torch_cuda):
+    """The production kernel over the whole sphere (the bench's stress workload): both polar caps
+    of the RING scheme in its 32-bit pixel arithmetic, every base face, stars within 0.8 degrees
+    of a pole (the reference's own angle chain), transverse angles far beyond the Taylor range
+    of the small-angle sin/cos -- pix and flags bit-exact against the oracle, columns to 1e-9,
+    and the same bytes from the generic kernel."""
+    n, seed = 1 << 21, 5
+    eng, _ = _fused_engine("wholesky")
+    out = eng.generate_observe(n, seed=seed, pix=True, export_draws=True)      # generic kernel
+    fused = eng.generate_observe(n, seed=seed, pix=True)                         # production kernel
+    _assert_same_bytes(torch_cuda, fused, out, fused.keys())
+    got = {k: v.cpu().numpy() for k, v in out.items() if k != "draws"}
+    ref = _oracle_fused("wholesky", eng.exported_draws(out))
+    z = np.sin(np.radians(got["dec"]))
+    assert (z > 2 / 3).mean() > 0.1 and (z < -2 / 3).mean() > 0.1 and (np.abs(z) >= 0.9999).sum() > 50
+    assert np.abs(got["phi2"]).max() > 90.0
+    assert np.array_equal(got["pix"], ref["pix"]), "pixel indices"
+    npix = 12 * int(eng.params.nside_pix) ** 2
+    assert got["pix"].min() < 0.001 * npix and got["pix"].max() > 0.999 * npix   # cap to cap
+    assert np.array_equal(got["flag_observed"].astype(bool), ref["flag_observed"])
+    for k in ("phi2", "dist", "mag_g", "mag_r", "ra", "dec", "mag_g_obs", "mag_r_obs",
+              "magerr_g", "magerr_r"):
+        assert_close(got[k], ref[k], RTOL, 1e-9, k)
+
+
 def test_fp32_map_option(torch_cuda):
     """StarEngine(map_dtype="f32") -- a labelled non-parity option: the survey maps rounded to
     fp32 and gathered as 16-byte packed records.  What it computes is the reference's chain on
