@@ -57,6 +57,16 @@ def stream_config(name):
                     distance_modulus=dict(center=dict(type="Line", slope=0.0, intercept=16.5),
                                           spread=dict(type="Constant", value=0.3), sampler="Gaussian"),
                     isochrone=dict(name="synthetic"))
+    if name == "gap":
+        # a density with an almost empty stretch: ~10^5 index thresholds of the phi1 sampler
+        # crowd into a few 32-bit words (one bucket of the word table saturates its count)
+        return dict(density=dict(type="Interpolation", xvals=[-10.0, -9.0, -8.99, 8.99, 9.0, 10.0],
+                                 yvals=[1.0, 1.0, 3e-6, 3e-6, 1.0, 1.0]),
+                    track=dict(center=dict(type="Line", slope=0.05, intercept=0.0),
+                               spread=dict(type="Constant", value=0.3), sampler="Gaussian"),
+                    distance_modulus=dict(center=dict(type="Line", slope=0.1, intercept=16.5),
+                                          spread=dict(type="Constant", value=0.05), sampler="Uniform"),
+                    isochrone=dict(name="synthetic"))
     if name in ("atlas_spline", "phoenix_spline"):
         f = "./data/patrick_2022_splines.csv"
         sn = name.split("_")[0]

@@ -258,6 +258,27 @@ def test_double_precision_normals_switch(torch_cuda):
         assert np.allclose(got[k], ref[k], rtol=1e-9, atol=1e-9, equal_nan=True), k
 
 
+def test_saturated_word_bucket(torch_cuda):
+    """A density with an almost empty stretch: tens of thousands of index thresholds of the phi1
+    sampler fall into one bucket of the 32-bit word table (count field saturated, binary search
+    over equal word thresholds).  Production kernel = generic kernel (double thresholds) = oracle."""
+    from stream_sim_b200.engine import WLUT_K_CAP
+    n, seed = 1 << 21, 9
+    eng, _ = _fused_engine("gap")
+    k = (eng.grid_wlut.cpu().numpy().view(np.uint32).reshape(-1, 4)[:, 0] >> 20)
+    assert k.max() == WLUT_K_CAP and int(eng.params.grid_wlut_n) > 0
+    out = eng.generate_observe(n, seed=seed, pix=True, export_draws=True)      # generic kernel
+    fused = eng.generate_observe(n, seed=seed, pix=True)                         # production kernel
+    _assert_same_bytes(torch_cuda, fused, out, fused.keys())
+    got = {k_: v.cpu().numpy() for k_, v in out.items() if k_ != "draws"}
+    ref = _oracle_fused("gap", eng.exported_draws(out))
+    assert np.array_equal(got["phi1"], ref["phi1"])
+    inside = np.abs(got["phi1"]) < 8.9
+    assert 0 < inside.sum() < 1e-3 * n                     # a few stars do land in the stretch
+    assert np.array_equal(got["pix"], ref["pix"])
+    assert np.array_equal(got["flag_observed"].astype(bool), ref["flag_observed"])
+
+
 def test_whole_sky_matches_oracle(torch_cuda):
     """The production kernel over the whole sphere (the bench's stress workload): both polar caps
     of the RING scheme in its 32-bit pixel arithmetic, every base face, stars within 0.8 degrees
