@@ -57,6 +57,13 @@ def stream_config(name):
                     distance_modulus=dict(center=dict(type="Line", slope=0.0, intercept=16.5),
                                           spread=dict(type="Constant", value=0.3), sampler="Gaussian"),
                     isochrone=dict(name="synthetic"))
+    if name == "tails":
+        # zero density at both ends: a quarter of the index thresholds sit at u = 0 (folded
+        # into the first bucket's step), a quarter are never reached
+        cfg = stream_config("gap")
+        cfg["density"] = dict(type="Interpolation", xvals=[-10.0, -5.0, -4.99, 4.99, 5.0, 10.0],
+                              yvals=[0.0, 0.0, 1.0, 1.0, 0.0, 0.0])
+        return cfg
     if name == "gap":
         # a density with an almost empty stretch: ~10^5 index thresholds of the phi1 sampler
         # crowd into a few 32-bit words (one bucket of the word table saturates its count)

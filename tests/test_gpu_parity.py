@@ -258,23 +258,34 @@ def test_double_precision_normals_switch(torch_cuda):
         assert np.allclose(got[k], ref[k], rtol=1e-9, atol=1e-9, equal_nan=True), k
 
 
-def test_saturated_word_bucket(torch_cuda):
-    """A density with an almost empty stretch: tens of thousands of index thresholds of the phi1
-    sampler fall into one bucket of the 32-bit word table (count field saturated, binary search
-    over equal word thresholds).  Production kernel = generic kernel (double thresholds) = oracle."""
+@pytest.mark.parametrize("cfg_name", ["gap", "tails"])
+def test_word_table_edge_densities(torch_cuda, cfg_name):
+    """Densities that stress the 32-bit word tables of the production kernel.  "gap": an almost
+    empty stretch -- tens of thousands of index thresholds of the phi1 sampler fall into one
+    bucket (count field saturated, binary search over word thresholds).  "tails": zero density
+    at both ends -- a quarter of the thresholds sit at u = 0 and are folded into the first
+    bucket's step, a quarter are never reached.  Production kernel = generic kernel (double
+    thresholds) = oracle."""
     from stream_sim_b200.engine import WLUT_K_CAP
     n, seed = 1 << 21, 9
-    eng, _ = _fused_engine("gap")
-    k = (eng.grid_wlut.cpu().numpy().view(np.uint32).reshape(-1, 4)[:, 0] >> 20)
-    assert k.max() == WLUT_K_CAP and int(eng.params.grid_wlut_n) > 0
+    eng, _ = _fused_engine(cfg_name)
+    assert int(eng.params.grid_wlut_n) > 0
+    lut = eng.grid_wlut.cpu().numpy().view(np.uint32).reshape(-1, 4)
+    if cfg_name == "gap":
+        assert (lut[:, 0] >> 20).max() == WLUT_K_CAP
+    else:
+        assert (lut[0, 0] & 0xFFFFF) > 20000                 # thresholds at or below zero
     out = eng.generate_observe(n, seed=seed, pix=True, export_draws=True)      # generic kernel
     fused = eng.generate_observe(n, seed=seed, pix=True)                         # production kernel
     _assert_same_bytes(torch_cuda, fused, out, fused.keys())
     got = {k_: v.cpu().numpy() for k_, v in out.items() if k_ != "draws"}
-    ref = _oracle_fused("gap", eng.exported_draws(out))
+    ref = _oracle_fused(cfg_name, eng.exported_draws(out))
     assert np.array_equal(got["phi1"], ref["phi1"])
-    inside = np.abs(got["phi1"]) < 8.9
-    assert 0 < inside.sum() < 1e-3 * n                     # a few stars do land in the stretch
+    if cfg_name == "gap":
+        inside = np.abs(got["phi1"]) < 8.9
+        assert 0 < inside.sum() < 1e-3 * n                 # a few stars do land in the stretch
+    else:
+        assert np.abs(got["phi1"]).max() <= 5.0
     assert np.array_equal(got["pix"], ref["pix"])
     assert np.array_equal(got["flag_observed"].astype(bool), ref["flag_observed"])
 
